@@ -1,0 +1,352 @@
+"""ctypes binding of lib/libtsdf_fusion.so (include/tsdf_fusion.h).
+
+Host-side mirror of the reference's depth-fusion driver (depth-fusion/demo.cu:72-216) for the
+test-suite and bench.py: the names follow the reference (`Integrate`, `invert_matrix`,
+`multiply_matrix`, `SaveVoxelGrid2SurfacePointCloud`, `ReadDepth`, `LoadMatrixFromFile`).
+There is no Python or CPU implementation behind any compute call: if the shared library is
+missing, or no CUDA device is usable, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "lib" / "libtsdf_fusion.so"
+
+TSDF_MAX_BATCH = 32
+
+# every extern "C" symbol include/tsdf_fusion.h declares
+EXPORTED_SYMBOLS = [
+    "tsdf_create", "tsdf_destroy", "tsdf_reset", "tsdf_synchronize", "tsdf_get_stats", "tsdf_reset_stats",
+    "tsdf_timer_start", "tsdf_timer_stop", "tsdf_integrate", "tsdf_integrate_batch",
+    "tsdf_integrate_batch_u16", "tsdf_download", "tsdf_upload", "tsdf_device_ptrs", "tsdf_extract_surface",
+    "tsdf_copy_surface", "tsdf_surface_device_ptr", "tsdf_write_ply", "tsdf_write_bin", "tsdf_load_matrix",
+    "tsdf_read_depth_png", "tsdf_read_depth_png_u16", "tsdf_depth_from_u16", "tsdf_multiply_matrix",
+    "tsdf_invert_matrix", "tsdf_Integrate", "tsdf_SaveVoxelGrid2SurfacePointCloud", "tsdf_last_error",
+    "tsdf_version", "tsdf_device_count", "tsdf_selftest_rounding",
+]
+
+
+class TsdfError(RuntimeError):
+    pass
+
+
+class VolumeDesc(C.Structure):
+    _fields_ = [
+        ("dim_x", C.c_int64), ("dim_y", C.c_int64), ("dim_z", C.c_int64),
+        ("z_begin", C.c_int64), ("z_end", C.c_int64),
+        ("origin_x", C.c_float), ("origin_y", C.c_float), ("origin_z", C.c_float),
+        ("voxel_size", C.c_float), ("trunc_margin", C.c_float),
+        ("im_width", C.c_int32), ("im_height", C.c_int32),
+        ("cam_K", C.c_float * 9),
+        ("device", C.c_int32), ("max_batch", C.c_int32), ("cull_level", C.c_int32), ("reserved0", C.c_int32),
+        ("stream", C.c_void_p), ("ext_tsdf", C.c_void_p), ("ext_weight", C.c_void_p),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("frames_integrated", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the engine; fails loudly when it has not been built (see __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise TsdfError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    fp, i64p = C.POINTER(C.c_float), C.POINTER(C.c_int64)
+    vp = C.c_void_p
+    sig = {
+        "tsdf_create": [C.POINTER(VolumeDesc), C.POINTER(vp)],
+        "tsdf_reset": [vp], "tsdf_synchronize": [vp],
+        "tsdf_get_stats": [vp, C.POINTER(Stats)], "tsdf_reset_stats": [vp],
+        "tsdf_timer_start": [vp], "tsdf_timer_stop": [vp, fp],
+        "tsdf_integrate": [vp, vp, vp],
+        "tsdf_integrate_batch": [vp, C.c_int32, vp, vp],
+        "tsdf_integrate_batch_u16": [vp, C.c_int32, vp, vp],
+        "tsdf_download": [vp, vp, vp], "tsdf_upload": [vp, vp, vp],
+        "tsdf_device_ptrs": [vp, C.POINTER(vp), C.POINTER(vp)],
+        "tsdf_extract_surface": [vp, C.c_float, C.c_float, i64p],
+        "tsdf_copy_surface": [vp, vp, C.c_int64],
+        "tsdf_surface_device_ptr": [vp, C.POINTER(vp), i64p],
+        "tsdf_write_ply": [C.c_char_p, vp, C.c_int64],
+        "tsdf_write_bin": [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,
+                           C.c_float, C.c_float, vp],
+        "tsdf_load_matrix": [C.c_char_p, C.c_int32, C.c_int32, vp],
+        "tsdf_read_depth_png": [C.c_char_p, C.c_int32, C.c_int32, vp],
+        "tsdf_read_depth_png_u16": [C.c_char_p, C.c_int32, C.c_int32, vp],
+        "tsdf_invert_matrix": [vp, vp],
+        "tsdf_Integrate": [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                           C.c_float, C.c_float, C.c_float, vp, vp, vp],
+        "tsdf_SaveVoxelGrid2SurfacePointCloud": [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                 C.c_float, C.c_float, vp, vp, C.c_float, C.c_float],
+        "tsdf_device_count": [C.POINTER(C.c_int32)],
+        "tsdf_selftest_rounding": [C.c_int32, i64p],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.tsdf_destroy.argtypes = [vp]
+    lib.tsdf_destroy.restype = None
+    lib.tsdf_multiply_matrix.argtypes = [vp, vp, vp]
+    lib.tsdf_multiply_matrix.restype = None
+    lib.tsdf_depth_from_u16.argtypes = [vp, C.c_int64, vp]
+    lib.tsdf_depth_from_u16.restype = None
+    lib.tsdf_last_error.restype = C.c_char_p
+    lib.tsdf_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise TsdfError(f"{what} failed (status {rc}): {load_library().tsdf_last_error().decode()}")
+
+
+def _f32(a, n=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} floats, got {a.size}")
+    return a
+
+
+def _ptr(a) -> int:
+    """Address of a numpy array, a torch tensor (host or CUDA) or a raw int."""
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    return int(a.ctypes.data)
+
+
+# ---- pose algebra / file helpers (host; reference names) ------------------------------------------
+
+def multiply_matrix(m1, m2) -> np.ndarray:
+    """depth-fusion/utils.hpp:89-109."""
+    a, b = _f32(m1, 16), _f32(m2, 16)
+    out = np.empty(16, np.float32)
+    load_library().tsdf_multiply_matrix(a.ctypes.data, b.ctypes.data, out.ctypes.data)
+    return out.reshape(4, 4)
+
+
+def invert_matrix(m):
+    """depth-fusion/utils.hpp:112-238.  Returns (ok, inverse)."""
+    a = _f32(m, 16)
+    out = np.zeros(16, np.float32)
+    ok = load_library().tsdf_invert_matrix(a.ctypes.data, out.ctypes.data)
+    return bool(ok), out.reshape(4, 4)
+
+
+def cam2base_from_world(base2world, cam2world) -> np.ndarray:
+    """depth-fusion/demo.cu:127-128,171: cam2base = inv(base2world) * cam2world."""
+    _, inv = invert_matrix(base2world)
+    return multiply_matrix(inv, cam2world)
+
+
+def LoadMatrixFromFile(path, rows, cols) -> np.ndarray:
+    out = np.empty(rows * cols, np.float32)
+    _check(load_library().tsdf_load_matrix(os.fsencode(path), rows, cols, out.ctypes.data), "tsdf_load_matrix")
+    return out.reshape(rows, cols)
+
+
+def ReadDepth(path, im_height, im_width) -> np.ndarray:
+    out = np.empty((im_height, im_width), np.float32)
+    _check(load_library().tsdf_read_depth_png(os.fsencode(path), im_height, im_width, out.ctypes.data),
+           "tsdf_read_depth_png")
+    return out
+
+
+def read_depth_png_u16(path, im_height, im_width) -> np.ndarray:
+    out = np.empty((im_height, im_width), np.uint16)
+    _check(load_library().tsdf_read_depth_png_u16(os.fsencode(path), im_height, im_width, out.ctypes.data),
+           "tsdf_read_depth_png_u16")
+    return out
+
+
+def depth_from_u16(mm) -> np.ndarray:
+    mm = np.ascontiguousarray(mm, dtype=np.uint16)
+    out = np.empty(mm.shape, np.float32)
+    load_library().tsdf_depth_from_u16(mm.ctypes.data, mm.size, out.ctypes.data)
+    return out
+
+
+def write_ply(path, xyz):
+    xyz = _f32(xyz)
+    _check(load_library().tsdf_write_ply(os.fsencode(path), xyz.ctypes.data, xyz.size // 3), "tsdf_write_ply")
+
+
+def write_bin(path, dims, origin, voxel_size, trunc_margin, tsdf):
+    t = _f32(tsdf, int(dims[0]) * int(dims[1]) * int(dims[2]))
+    _check(load_library().tsdf_write_bin(os.fsencode(path), dims[0], dims[1], dims[2], origin[0], origin[1],
+                                         origin[2], voxel_size, trunc_margin, t.ctypes.data), "tsdf_write_bin")
+
+
+def SaveVoxelGrid2SurfacePointCloud(file_name, dim_x, dim_y, dim_z, voxel_size, ox, oy, oz, tsdf, weight,
+                                    tsdf_thresh, weight_thresh):
+    """depth-fusion/utils.hpp:14-17 argument list; host arrays in, tsdf.ply out (scan on the GPU)."""
+    n = dim_x * dim_y * dim_z
+    t, w = _f32(tsdf, n), _f32(weight, n)
+    _check(load_library().tsdf_SaveVoxelGrid2SurfacePointCloud(
+        os.fsencode(file_name), dim_x, dim_y, dim_z, voxel_size, ox, oy, oz, t.ctypes.data, w.ctypes.data,
+        tsdf_thresh, weight_thresh), "tsdf_SaveVoxelGrid2SurfacePointCloud")
+
+
+def Integrate(cam_K, cam2base, depth_im, im_height, im_width, dim_x, dim_y, dim_z, ox, oy, oz, voxel_size,
+              trunc_margin, tsdf, weight, stream=0):
+    """depth-fusion/demo.cu:18-22 argument list; every pointer is a DEVICE pointer (int / torch CUDA tensor)."""
+    _check(load_library().tsdf_Integrate(_ptr(cam_K), _ptr(cam2base), _ptr(depth_im), im_height, im_width, dim_x,
+                                         dim_y, dim_z, ox, oy, oz, voxel_size, trunc_margin, _ptr(tsdf),
+                                         _ptr(weight), stream), "tsdf_Integrate")
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    _check(load_library().tsdf_device_count(C.byref(n)), "tsdf_device_count")
+    return n.value
+
+
+def selftest_rounding(device=0) -> int:
+    n = C.c_int64(-1)
+    _check(load_library().tsdf_selftest_rounding(device, C.byref(n)), "tsdf_selftest_rounding")
+    return n.value
+
+
+# ---- the engine handle -------------------------------------------------------------------------------
+
+class Volume:
+    """A TSDF volume (or one z-slab of it) resident in the HBM of one GPU."""
+
+    def __init__(self, dims, origin, voxel_size, trunc_margin, cam_K, im_size=(640, 480), z_range=None,
+                 device=0, max_batch=0, cull_level=-1, stream=0, ext_tsdf=None, ext_weight=None):
+        self._lib = load_library()
+        d = VolumeDesc()
+        d.dim_x, d.dim_y, d.dim_z = (int(v) for v in dims)
+        d.z_begin, d.z_end = (0, d.dim_z) if z_range is None else (int(z_range[0]), int(z_range[1]))
+        d.origin_x, d.origin_y, d.origin_z = (float(v) for v in origin)
+        d.voxel_size, d.trunc_margin = float(voxel_size), float(trunc_margin)
+        d.im_width, d.im_height = int(im_size[0]), int(im_size[1])
+        d.cam_K = (C.c_float * 9)(*[float(v) for v in np.asarray(cam_K, np.float32).ravel()])
+        d.device, d.max_batch, d.cull_level = int(device), int(max_batch), int(cull_level)
+        d.stream = stream or None
+        d.ext_tsdf = _ptr(ext_tsdf) if ext_tsdf is not None else None
+        d.ext_weight = _ptr(ext_weight) if ext_weight is not None else None
+        self.desc = d
+        self._h = C.c_void_p()
+        _check(self._lib.tsdf_create(C.byref(d), C.byref(self._h)), "tsdf_create")
+        self.dims = (d.dim_x, d.dim_y, d.dim_z)
+        self.z_range = (d.z_begin, d.z_end)
+        self.n_voxels = (d.z_end - d.z_begin) * d.dim_y * d.dim_x
+        self.frame_px = d.im_width * d.im_height
+        self._keepalive = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tsdf_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self):
+        _check(self._lib.tsdf_reset(self._h), "tsdf_reset")
+
+    def synchronize(self):
+        _check(self._lib.tsdf_synchronize(self._h), "tsdf_synchronize")
+        self._keepalive.clear()
+
+    def integrate(self, depth, cam2base):
+        """One reference launch (demo.cu:173-182). depth: numpy (host) or torch tensor (host / CUDA)."""
+        self.integrate_batch(depth, np.asarray(cam2base, np.float32).reshape(1, 16), n_frames=1)
+
+    def integrate_batch(self, depth_frames, cam2base, n_frames=None):
+        poses = _f32(cam2base)
+        n = poses.size // 16 if n_frames is None else int(n_frames)
+        u16 = False
+        if isinstance(depth_frames, np.ndarray):
+            u16 = depth_frames.dtype == np.uint16
+            depth_frames = np.ascontiguousarray(depth_frames, dtype=np.uint16 if u16 else np.float32)
+            size = depth_frames.size
+        else:  # torch tensor
+            import torch
+            u16 = depth_frames.dtype in (torch.uint16, torch.int16)
+            if not depth_frames.is_contiguous():
+                raise ValueError("depth tensor must be contiguous")
+            size = depth_frames.numel()
+        if size < n * self.frame_px or poses.size < 16 * n:
+            raise ValueError("depth_frames / cam2base smaller than n_frames")
+        fn = self._lib.tsdf_integrate_batch_u16 if u16 else self._lib.tsdf_integrate_batch
+        self._keepalive.append((depth_frames, poses))  # async H2D may still read them
+        _check(fn(self._h, n, _ptr(depth_frames), poses.ctypes.data), "tsdf_integrate_batch")
+
+    def download(self, want_tsdf=True, want_weight=True):
+        nz = self.z_range[1] - self.z_range[0]
+        shape = (nz, self.dims[1], self.dims[0])
+        t = np.empty(shape, np.float32) if want_tsdf else None
+        w = np.empty(shape, np.float32) if want_weight else None
+        _check(self._lib.tsdf_download(self._h, t.ctypes.data if want_tsdf else None,
+                                       w.ctypes.data if want_weight else None), "tsdf_download")
+        self._keepalive.clear()
+        return t, w
+
+    def upload(self, tsdf=None, weight=None):
+        t = _f32(tsdf, self.n_voxels) if tsdf is not None else None
+        w = _f32(weight, self.n_voxels) if weight is not None else None
+        _check(self._lib.tsdf_upload(self._h, t.ctypes.data if t is not None else None,
+                                     w.ctypes.data if w is not None else None), "tsdf_upload")
+
+    def device_ptrs(self):
+        t, w = C.c_void_p(), C.c_void_p()
+        _check(self._lib.tsdf_device_ptrs(self._h, C.byref(t), C.byref(w)), "tsdf_device_ptrs")
+        return t.value, w.value
+
+    def extract_surface_count(self, tsdf_thresh=0.2, weight_thresh=1.0) -> int:
+        n = C.c_int64(0)
+        _check(self._lib.tsdf_extract_surface(self._h, tsdf_thresh, weight_thresh, C.byref(n)),
+               "tsdf_extract_surface")
+        return n.value
+
+    def extract_surface(self, tsdf_thresh=0.2, weight_thresh=1.0, out=None) -> np.ndarray:
+        """utils.hpp:20-53 thresholds default to demo.cu:194's 0.2f / 1.0f. Returns (N, 3) float32."""
+        n = self.extract_surface_count(tsdf_thresh, weight_thresh)
+        if out is None:
+            out = np.empty((n, 3), np.float32)
+        _check(self._lib.tsdf_copy_surface(self._h, _ptr(out), n), "tsdf_copy_surface")
+        return out[:n] if isinstance(out, np.ndarray) else out
+
+    def surface_device_ptr(self):
+        p, n = C.c_void_p(), C.c_int64(0)
+        _check(self._lib.tsdf_surface_device_ptr(self._h, C.byref(p), C.byref(n)), "tsdf_surface_device_ptr")
+        return p.value, n.value
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(self._lib.tsdf_get_stats(self._h, C.byref(s)), "tsdf_get_stats")
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def reset_stats(self):
+        _check(self._lib.tsdf_reset_stats(self._h), "tsdf_reset_stats")
+
+    def timer_start(self):
+        _check(self._lib.tsdf_timer_start(self._h), "tsdf_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        _check(self._lib.tsdf_timer_stop(self._h, C.byref(ms)), "tsdf_timer_stop")
+        return ms.value

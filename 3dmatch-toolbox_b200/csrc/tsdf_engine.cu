@@ -1,0 +1,550 @@
+// tsdf_engine.cu -- C-ABI implementation (include/tsdf_fusion.h): engine handle, host<->device
+// staging, launch sequencing.  All arithmetic lives in tsdf_kernels.cu (device) and
+// tsdf_host.cpp (pose algebra / file formats); there is no CPU fallback for the compute path.
+#include "tsdf_fusion.h"
+#include "tsdf_kernels.h"
+#include "tsdf_host.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      return set_err(TSDF_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int kSlots = 3;  // staging ring depth for host-resident input
+
+}  // namespace
+
+void tsdf_set_error_text(const char* text) { snprintf(g_err, sizeof g_err, "%s", text); }
+
+struct tsdf_volume {
+  tsdf_volume_desc d;
+  int64_t nz = 0, n_vox = 0, frame_px = 0;
+  int batch = 0, cull = 2;
+  float* tsdf = nullptr;
+  float* weight = nullptr;
+  bool owns_volume = false;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  bool owns_stream = false;
+  // staging ring (allocated on first host-input integrate)
+  float* dev_depth[kSlots] = {};
+  float* pin_depth[kSlots] = {};
+  uint16_t* dev_mm[kSlots] = {};
+  uint16_t* pin_mm[kSlots] = {};
+  cudaEvent_t ev_copied[kSlots] = {}, ev_consumed[kSlots] = {};
+  bool slot_busy[kSlots] = {};
+  int64_t ring_pos = 0;
+  // surface extraction
+  unsigned long long* tile_offsets = nullptr;
+  int64_t tile_cap = 0;
+  float* xyz = nullptr;
+  int64_t xyz_cap = 0, n_points = -1;
+  // timing / stats
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  tsdf_stats stats = {};
+  float max_abs_corner = 0.f;
+};
+
+namespace {
+
+int use_device(const tsdf_volume* v) {
+  CK(cudaSetDevice(v->d.device));
+  return TSDF_OK;
+}
+
+// Margins for the conservative frustum culls of integrate_kernel.  delta bounds the distance
+// between any voxel's fp32 camera coordinates (as the kernel computes them) and the exact affine
+// map of its position; the cull half-spaces are pushed out by a multiple of it.
+void make_cull_margins(const tsdf_volume* v, const tsdf::FramePose* poses, int n, tsdf::IntegrateParams* p) {
+  float rmax = 1.f, tmax = 0.f;
+  bool finite = true;
+  for (int f = 0; f < n; ++f) {
+    const float* m = &poses[f].m0;
+    for (int i = 0; i < 9; ++i) { rmax = fmaxf(rmax, fabsf(m[i])); finite = finite && std::isfinite(m[i]); }
+    for (int i = 9; i < 12; ++i) { tmax = fmaxf(tmax, fabsf(m[i])); finite = finite && std::isfinite(m[i]); }
+  }
+  const float coord = v->max_abs_corner + tmax;
+  const float delta = 64.f * FLT_EPSILON * 3.f * rmax * (coord + 1.f);
+  if (!finite || !std::isfinite(delta)) {
+    p->cull_level = 0;
+    p->cull_z = p->cull_gx = p->cull_gy = 0.f;
+    return;
+  }
+  p->cull_z = 4.f * delta;
+  p->cull_gx = 4.f * delta * (fabsf(p->fx) + fabsf(p->cx) + (float)p->im_w + 4.f);
+  p->cull_gy = 4.f * delta * (fabsf(p->fy) + fabsf(p->cy) + (float)p->im_h + 4.f);
+}
+
+void fill_params(const tsdf_volume* v, tsdf::IntegrateParams* p) {
+  memset(p, 0, sizeof *p);
+  p->tsdf = v->tsdf;
+  p->weight = v->weight;
+  p->frame_stride = v->frame_px;
+  p->dim_x = (int)v->d.dim_x;
+  p->dim_y = (int)v->d.dim_y;
+  p->nz = (int)v->nz;
+  p->z_begin = (int)v->d.z_begin;
+  p->ox = v->d.origin_x; p->oy = v->d.origin_y; p->oz = v->d.origin_z;
+  p->voxel_size = v->d.voxel_size;
+  p->trunc_margin = v->d.trunc_margin;
+  p->fx = v->d.cam_K[0]; p->cx = v->d.cam_K[2]; p->fy = v->d.cam_K[4]; p->cy = v->d.cam_K[5];
+  p->im_w = v->d.im_width; p->im_h = v->d.im_height;
+  p->cull_level = v->cull;
+}
+
+void pose_from_cam2base(const float* c, tsdf::FramePose* o) {
+  o->m0 = c[0]; o->m1 = c[1]; o->m2 = c[2];
+  o->m4 = c[4]; o->m5 = c[5]; o->m6 = c[6];
+  o->m8 = c[8]; o->m9 = c[9]; o->m10 = c[10];
+  o->tx = c[3]; o->ty = c[7]; o->tz = c[11];
+}
+
+// Launch one pass over the slab for `n` (<= batch) frames whose depth is on the device.
+int launch_chunk(tsdf_volume* v, const float* dev_depth, const float* cam2base, int n) {
+  tsdf::IntegrateParams p;
+  fill_params(v, &p);
+  p.depth = dev_depth;
+  p.n_frames = n;
+  for (int f = 0; f < n; ++f) pose_from_cam2base(cam2base + 16 * f, &p.pose[f]);
+  make_cull_margins(v, p.pose, n, &p);
+  CK(tsdf::launch_integrate(p, v->stream));
+  v->stats.kernel_launches += 1;
+  v->stats.frames_integrated += n;
+  v->n_points = -1;
+  return TSDF_OK;
+}
+
+int ensure_ring(tsdf_volume* v, bool u16) {
+  const size_t px = (size_t)v->frame_px * v->batch;
+  for (int s = 0; s < kSlots; ++s) {
+    if (!v->dev_depth[s]) CK(cudaMalloc(&v->dev_depth[s], px * sizeof(float)));
+    if (!v->ev_copied[s]) CK(cudaEventCreateWithFlags(&v->ev_copied[s], cudaEventDisableTiming));
+    if (!v->ev_consumed[s]) CK(cudaEventCreateWithFlags(&v->ev_consumed[s], cudaEventDisableTiming));
+    if (u16 && !v->dev_mm[s]) CK(cudaMalloc(&v->dev_mm[s], px * sizeof(uint16_t)));
+  }
+  if (!v->copy_stream) CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
+  return TSDF_OK;
+}
+
+int ensure_pinned(tsdf_volume* v, bool u16) {
+  const size_t px = (size_t)v->frame_px * v->batch;
+  for (int s = 0; s < kSlots; ++s) {
+    if (!u16 && !v->pin_depth[s]) CK(cudaHostAlloc(&v->pin_depth[s], px * sizeof(float), cudaHostAllocDefault));
+    if (u16 && !v->pin_mm[s]) CK(cudaHostAlloc(&v->pin_mm[s], px * sizeof(uint16_t), cudaHostAllocDefault));
+  }
+  return TSDF_OK;
+}
+
+enum class MemKind { Device, PinnedHost, PageableHost };
+
+MemKind classify(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return MemKind::PageableHost;
+  }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return MemKind::Device;
+  if (a.type == cudaMemoryTypeHost) return MemKind::PinnedHost;
+  return MemKind::PageableHost;
+}
+
+// Host-resident input: K-frame chunks are copied on copy_stream into a ring of device buffers
+// while the previous chunk is being fused on the compute stream.
+template <typename Src>
+int integrate_from_host(tsdf_volume* v, int n_frames, const Src* src, const float* cam2base, MemKind kind) {
+  constexpr bool u16 = sizeof(Src) == 2;
+  int rc = ensure_ring(v, u16);
+  if (rc) return rc;
+  if (kind == MemKind::PageableHost && (rc = ensure_pinned(v, u16))) return rc;
+  for (int f0 = 0; f0 < n_frames; f0 += v->batch) {
+    const int n = (n_frames - f0 < v->batch) ? n_frames - f0 : v->batch;
+    const int s = (int)(v->ring_pos++ % kSlots);
+    const size_t elems = (size_t)n * v->frame_px;
+    const Src* chunk = src + (size_t)f0 * v->frame_px;
+    if (v->slot_busy[s]) {
+      // the pinned staging buffer and the device slot are reused: wait for their last consumer
+      if (kind == MemKind::PageableHost) CK(cudaEventSynchronize(v->ev_consumed[s]));
+      CK(cudaStreamWaitEvent(v->copy_stream, v->ev_consumed[s], 0));
+    }
+    const void* from = chunk;
+    if (kind == MemKind::PageableHost) {
+      void* pin = u16 ? (void*)v->pin_mm[s] : (void*)v->pin_depth[s];
+      memcpy(pin, chunk, elems * sizeof(Src));
+      from = pin;
+    }
+    void* to = u16 ? (void*)v->dev_mm[s] : (void*)v->dev_depth[s];
+    CK(cudaMemcpyAsync(to, from, elems * sizeof(Src), cudaMemcpyHostToDevice, v->copy_stream));
+    v->stats.h2d_bytes += (int64_t)(elems * sizeof(Src));
+    CK(cudaEventRecord(v->ev_copied[s], v->copy_stream));
+    CK(cudaStreamWaitEvent(v->stream, v->ev_copied[s], 0));
+    if (u16) {
+      CK(tsdf::launch_depth_from_u16(v->dev_mm[s], v->dev_depth[s], (int64_t)elems, v->stream));
+      v->stats.kernel_launches += 1;
+    }
+    rc = launch_chunk(v, v->dev_depth[s], cam2base + 16 * (size_t)f0, n);
+    if (rc) return rc;
+    CK(cudaEventRecord(v->ev_consumed[s], v->stream));
+    v->slot_busy[s] = true;
+  }
+  return TSDF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tsdf_last_error(void) { return g_err; }
+const char* tsdf_version(void) { return "tsdf-fusion-b200 0.1 (sm_100a)"; }
+
+int tsdf_device_count(int32_t* count) {
+  if (!count) return set_err(TSDF_ERR_ARG, "count is NULL");
+  int n = 0;
+  CK(cudaGetDeviceCount(&n));
+  *count = n;
+  return TSDF_OK;
+}
+
+int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
+  if (!desc || !out) return set_err(TSDF_ERR_ARG, "desc/out is NULL");
+  *out = nullptr;
+  tsdf_volume_desc d = *desc;
+  if (d.dim_x <= 0 || d.dim_y <= 0 || d.dim_z <= 0) return set_err(TSDF_ERR_ARG, "grid dimensions must be positive");
+  if (d.dim_x > INT32_MAX / 2 || d.dim_y > INT32_MAX / 2 || d.dim_z > INT32_MAX / 2)
+    return set_err(TSDF_ERR_ARG, "grid dimension too large");
+  if (d.z_begin == 0 && d.z_end == 0) d.z_end = d.dim_z;
+  if (d.z_begin < 0 || d.z_end > d.dim_z || d.z_begin >= d.z_end)
+    return set_err(TSDF_ERR_ARG, "z slab [%lld, %lld) outside [0, %lld)", (long long)d.z_begin, (long long)d.z_end,
+                   (long long)d.dim_z);
+  if (d.im_width <= 0 || d.im_height <= 0) return set_err(TSDF_ERR_ARG, "image size must be positive");
+  if ((int64_t)d.im_width * d.im_height > INT32_MAX) return set_err(TSDF_ERR_ARG, "image too large");
+  if (d.max_batch < 0 || d.max_batch > TSDF_MAX_BATCH) return set_err(TSDF_ERR_ARG, "max_batch out of range");
+  if ((d.ext_tsdf == nullptr) != (d.ext_weight == nullptr))
+    return set_err(TSDF_ERR_ARG, "ext_tsdf and ext_weight must be given together");
+
+  tsdf_volume* v = new (std::nothrow) tsdf_volume();
+  if (!v) return set_err(TSDF_ERR_ARG, "out of host memory");
+  v->d = d;
+  v->nz = d.z_end - d.z_begin;
+  v->n_vox = v->nz * d.dim_y * d.dim_x;
+  v->frame_px = (int64_t)d.im_width * d.im_height;
+  v->batch = d.max_batch ? d.max_batch : 16;
+  v->cull = (d.cull_level < 0 || d.cull_level > 2) ? 2 : d.cull_level;
+  {
+    const float ex = fmaxf(fabsf(d.origin_x), fabsf(d.origin_x + (float)d.dim_x * d.voxel_size));
+    const float ey = fmaxf(fabsf(d.origin_y), fabsf(d.origin_y + (float)d.dim_y * d.voxel_size));
+    const float ez = fmaxf(fabsf(d.origin_z), fabsf(d.origin_z + (float)d.dim_z * d.voxel_size));
+    v->max_abs_corner = fmaxf(ex, fmaxf(ey, ez));
+  }
+  int rc = TSDF_OK;
+  auto fail = [&](int code) { tsdf_destroy(v); return code; };
+  cudaError_t e = cudaSetDevice(d.device);
+  if (e != cudaSuccess)
+    return fail(set_err(TSDF_ERR_CUDA, "cudaSetDevice(%d): %s (no CPU fallback exists)", d.device, cudaGetErrorString(e)));
+  if (d.stream) {
+    v->stream = (cudaStream_t)d.stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail(set_err(TSDF_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)));
+    v->owns_stream = true;
+  }
+  if (d.ext_tsdf) {
+    v->tsdf = d.ext_tsdf;
+    v->weight = d.ext_weight;
+  } else {
+    e = cudaMalloc(&v->tsdf, (size_t)v->n_vox * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&v->weight, (size_t)v->n_vox * sizeof(float));
+    if (e != cudaSuccess)
+      return fail(set_err(TSDF_ERR_CUDA, "cudaMalloc of %lld voxels: %s", (long long)v->n_vox, cudaGetErrorString(e)));
+    v->owns_volume = true;
+  }
+  e = cudaEventCreate(&v->t0);
+  if (e == cudaSuccess) e = cudaEventCreate(&v->t1);
+  if (e != cudaSuccess) return fail(set_err(TSDF_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)));
+  if (v->owns_volume && (rc = tsdf_reset(v)) != TSDF_OK) return fail(rc);
+  *out = v;
+  return TSDF_OK;
+}
+
+void tsdf_destroy(tsdf_volume* v) {
+  if (!v) return;
+  cudaSetDevice(v->d.device);
+  if (v->stream) cudaStreamSynchronize(v->stream);
+  if (v->copy_stream) { cudaStreamSynchronize(v->copy_stream); cudaStreamDestroy(v->copy_stream); }
+  for (int s = 0; s < kSlots; ++s) {
+    cudaFree(v->dev_depth[s]);
+    cudaFree(v->dev_mm[s]);
+    if (v->pin_depth[s]) cudaFreeHost(v->pin_depth[s]);
+    if (v->pin_mm[s]) cudaFreeHost(v->pin_mm[s]);
+    if (v->ev_copied[s]) cudaEventDestroy(v->ev_copied[s]);
+    if (v->ev_consumed[s]) cudaEventDestroy(v->ev_consumed[s]);
+  }
+  if (v->owns_volume) { cudaFree(v->tsdf); cudaFree(v->weight); }
+  cudaFree(v->tile_offsets);
+  cudaFree(v->xyz);
+  if (v->t0) cudaEventDestroy(v->t0);
+  if (v->t1) cudaEventDestroy(v->t1);
+  if (v->owns_stream && v->stream) cudaStreamDestroy(v->stream);
+  cudaGetLastError();
+  delete v;
+}
+
+int tsdf_reset(tsdf_volume* v) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (int rc = use_device(v)) return rc;
+  CK(tsdf::launch_fill(v->tsdf, v->weight, v->n_vox, v->stream));
+  v->stats.kernel_launches += 1;
+  v->n_points = -1;
+  return TSDF_OK;
+}
+
+int tsdf_synchronize(tsdf_volume* v) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (int rc = use_device(v)) return rc;
+  if (v->copy_stream) CK(cudaStreamSynchronize(v->copy_stream));
+  CK(cudaStreamSynchronize(v->stream));
+  return TSDF_OK;
+}
+
+int tsdf_get_stats(tsdf_volume* v, tsdf_stats* out) {
+  if (!v || !out) return set_err(TSDF_ERR_ARG, "NULL argument");
+  *out = v->stats;
+  return TSDF_OK;
+}
+
+int tsdf_reset_stats(tsdf_volume* v) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  v->stats = tsdf_stats{};
+  return TSDF_OK;
+}
+
+int tsdf_timer_start(tsdf_volume* v) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (int rc = use_device(v)) return rc;
+  CK(cudaEventRecord(v->t0, v->stream));
+  return TSDF_OK;
+}
+
+int tsdf_timer_stop(tsdf_volume* v, float* elapsed_ms) {
+  if (!v || !elapsed_ms) return set_err(TSDF_ERR_ARG, "NULL argument");
+  if (int rc = use_device(v)) return rc;
+  CK(cudaEventRecord(v->t1, v->stream));
+  CK(cudaEventSynchronize(v->t1));
+  CK(cudaEventElapsedTime(elapsed_ms, v->t0, v->t1));
+  return TSDF_OK;
+}
+
+int tsdf_integrate(tsdf_volume* v, const float* depth, const float* cam2base) {
+  return tsdf_integrate_batch(v, 1, depth, cam2base);
+}
+
+int tsdf_integrate_batch(tsdf_volume* v, int32_t n_frames, const float* depth_frames, const float* cam2base) {
+  if (!v || !depth_frames || !cam2base) return set_err(TSDF_ERR_ARG, "NULL argument");
+  if (n_frames < 0) return set_err(TSDF_ERR_ARG, "n_frames < 0");
+  if (int rc = use_device(v)) return rc;
+  const MemKind kind = classify(depth_frames);
+  if (kind == MemKind::Device) {
+    for (int f0 = 0; f0 < n_frames; f0 += v->batch) {
+      const int n = (n_frames - f0 < v->batch) ? n_frames - f0 : v->batch;
+      if (int rc = launch_chunk(v, depth_frames + (size_t)f0 * v->frame_px, cam2base + 16 * (size_t)f0, n)) return rc;
+    }
+    return TSDF_OK;
+  }
+  return integrate_from_host<float>(v, n_frames, depth_frames, cam2base, kind);
+}
+
+int tsdf_integrate_batch_u16(tsdf_volume* v, int32_t n_frames, const uint16_t* depth_mm, const float* cam2base) {
+  if (!v || !depth_mm || !cam2base) return set_err(TSDF_ERR_ARG, "NULL argument");
+  if (n_frames < 0) return set_err(TSDF_ERR_ARG, "n_frames < 0");
+  if (int rc = use_device(v)) return rc;
+  const MemKind kind = classify(depth_mm);
+  if (kind == MemKind::Device) {
+    if (int rc = ensure_ring(v, true)) return rc;
+    for (int f0 = 0; f0 < n_frames; f0 += v->batch) {
+      const int n = (n_frames - f0 < v->batch) ? n_frames - f0 : v->batch;
+      const int s = (int)(v->ring_pos++ % kSlots);
+      CK(tsdf::launch_depth_from_u16(depth_mm + (size_t)f0 * v->frame_px, v->dev_depth[s], (int64_t)n * v->frame_px,
+                                     v->stream));
+      v->stats.kernel_launches += 1;
+      if (int rc = launch_chunk(v, v->dev_depth[s], cam2base + 16 * (size_t)f0, n)) return rc;
+    }
+    return TSDF_OK;
+  }
+  return integrate_from_host<uint16_t>(v, n_frames, depth_mm, cam2base, kind);
+}
+
+int tsdf_download(tsdf_volume* v, float* tsdf_host, float* weight_host) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (int rc = tsdf_synchronize(v)) return rc;
+  const size_t bytes = (size_t)v->n_vox * sizeof(float);
+  if (tsdf_host) { CK(cudaMemcpy(tsdf_host, v->tsdf, bytes, cudaMemcpyDeviceToHost)); v->stats.d2h_bytes += bytes; }
+  if (weight_host) { CK(cudaMemcpy(weight_host, v->weight, bytes, cudaMemcpyDeviceToHost)); v->stats.d2h_bytes += bytes; }
+  return TSDF_OK;
+}
+
+int tsdf_upload(tsdf_volume* v, const float* tsdf_host, const float* weight_host) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (int rc = tsdf_synchronize(v)) return rc;
+  const size_t bytes = (size_t)v->n_vox * sizeof(float);
+  if (tsdf_host) { CK(cudaMemcpy(v->tsdf, tsdf_host, bytes, cudaMemcpyHostToDevice)); v->stats.h2d_bytes += bytes; }
+  if (weight_host) { CK(cudaMemcpy(v->weight, weight_host, bytes, cudaMemcpyHostToDevice)); v->stats.h2d_bytes += bytes; }
+  v->n_points = -1;
+  return TSDF_OK;
+}
+
+int tsdf_device_ptrs(tsdf_volume* v, float** tsdf_dev, float** weight_dev) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (tsdf_dev) *tsdf_dev = v->tsdf;
+  if (weight_dev) *weight_dev = v->weight;
+  return TSDF_OK;
+}
+
+int tsdf_extract_surface(tsdf_volume* v, float tsdf_thresh, float weight_thresh, int64_t* n_points) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (int rc = use_device(v)) return rc;
+  const int64_t n_tiles = (v->n_vox + tsdf::kExtractTile - 1) / tsdf::kExtractTile;
+  if (v->tile_cap < n_tiles + 1) {
+    cudaFree(v->tile_offsets);
+    v->tile_offsets = nullptr;
+    v->tile_cap = 0;
+    CK(cudaMalloc(&v->tile_offsets, (size_t)(n_tiles + 1) * sizeof(unsigned long long)));
+    v->tile_cap = n_tiles + 1;
+  }
+  tsdf::ExtractParams p;
+  p.tsdf = v->tsdf; p.weight = v->weight; p.n = v->n_vox;
+  p.dim_x = (int)v->d.dim_x; p.dim_y = (int)v->d.dim_y; p.z_begin = (int)v->d.z_begin;
+  p.ox = v->d.origin_x; p.oy = v->d.origin_y; p.oz = v->d.origin_z; p.voxel_size = v->d.voxel_size;
+  p.tsdf_thresh = tsdf_thresh; p.weight_thresh = weight_thresh;
+  CK(tsdf::launch_extract_count(p, v->tile_offsets, n_tiles, v->stream));
+  CK(tsdf::launch_extract_scan(v->tile_offsets, n_tiles, v->tile_offsets + n_tiles, v->stream));
+  v->stats.kernel_launches += 2;
+  unsigned long long total = 0;
+  CK(cudaMemcpyAsync(&total, v->tile_offsets + n_tiles, sizeof total, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaStreamSynchronize(v->stream));
+  v->stats.d2h_bytes += sizeof total;
+  if ((int64_t)total > v->xyz_cap) {
+    cudaFree(v->xyz);
+    v->xyz = nullptr;
+    v->xyz_cap = 0;
+    CK(cudaMalloc(&v->xyz, (size_t)total * 3 * sizeof(float)));
+    v->xyz_cap = (int64_t)total;
+  }
+  if (total > 0) {
+    CK(tsdf::launch_extract_emit(p, v->tile_offsets, n_tiles, v->xyz, v->stream));
+    v->stats.kernel_launches += 1;
+  }
+  v->n_points = (int64_t)total;
+  if (n_points) *n_points = (int64_t)total;
+  return TSDF_OK;
+}
+
+int tsdf_copy_surface(tsdf_volume* v, float* xyz_host, int64_t capacity_points) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (v->n_points < 0) return set_err(TSDF_ERR_STATE, "tsdf_extract_surface has not been called since the last update");
+  if (capacity_points < v->n_points) return set_err(TSDF_ERR_ARG, "capacity %lld < %lld points", (long long)capacity_points, (long long)v->n_points);
+  if (v->n_points == 0) return TSDF_OK;
+  if (!xyz_host) return set_err(TSDF_ERR_ARG, "xyz_host is NULL");
+  if (int rc = use_device(v)) return rc;
+  const size_t bytes = (size_t)v->n_points * 3 * sizeof(float);
+  CK(cudaMemcpyAsync(xyz_host, v->xyz, bytes, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaStreamSynchronize(v->stream));
+  v->stats.d2h_bytes += bytes;
+  return TSDF_OK;
+}
+
+int tsdf_surface_device_ptr(tsdf_volume* v, float** xyz_dev, int64_t* n_points) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (v->n_points < 0) return set_err(TSDF_ERR_STATE, "tsdf_extract_surface has not been called since the last update");
+  if (xyz_dev) *xyz_dev = v->xyz;
+  if (n_points) *n_points = v->n_points;
+  return TSDF_OK;
+}
+
+int tsdf_Integrate(const float* cam_K, const float* cam2base, const float* depth_im, int im_height, int im_width,
+                   int voxel_grid_dim_x, int voxel_grid_dim_y, int voxel_grid_dim_z, float voxel_grid_origin_x,
+                   float voxel_grid_origin_y, float voxel_grid_origin_z, float voxel_size, float trunc_margin,
+                   float* voxel_grid_TSDF, float* voxel_grid_weight, void* stream) {
+  if (!cam_K || !cam2base || !depth_im || !voxel_grid_TSDF || !voxel_grid_weight)
+    return set_err(TSDF_ERR_ARG, "NULL device pointer");
+  if (im_height <= 0 || im_width <= 0 || voxel_grid_dim_x <= 0 || voxel_grid_dim_y <= 0 || voxel_grid_dim_z <= 0)
+    return set_err(TSDF_ERR_ARG, "non-positive size");
+  tsdf::IntegrateParams p;
+  memset(&p, 0, sizeof p);
+  p.tsdf = voxel_grid_TSDF; p.weight = voxel_grid_weight; p.depth = depth_im;
+  p.frame_stride = (int64_t)im_height * im_width;
+  p.dim_x = voxel_grid_dim_x; p.dim_y = voxel_grid_dim_y; p.nz = voxel_grid_dim_z; p.z_begin = 0;
+  p.ox = voxel_grid_origin_x; p.oy = voxel_grid_origin_y; p.oz = voxel_grid_origin_z;
+  p.voxel_size = voxel_size; p.trunc_margin = trunc_margin;
+  p.im_w = im_width; p.im_h = im_height;
+  CK(tsdf::launch_integrate_devpose(p, cam_K, cam2base, (cudaStream_t)stream));
+  return TSDF_OK;
+}
+
+int tsdf_SaveVoxelGrid2SurfacePointCloud(const char* file_name, int voxel_grid_dim_x, int voxel_grid_dim_y,
+                                         int voxel_grid_dim_z, float voxel_size, float voxel_grid_origin_x,
+                                         float voxel_grid_origin_y, float voxel_grid_origin_z,
+                                         const float* voxel_grid_TSDF, const float* voxel_grid_weight,
+                                         float tsdf_thresh, float weight_thresh) {
+  if (!file_name || !voxel_grid_TSDF || !voxel_grid_weight) return set_err(TSDF_ERR_ARG, "NULL argument");
+  tsdf_volume_desc d;
+  memset(&d, 0, sizeof d);
+  d.dim_x = voxel_grid_dim_x; d.dim_y = voxel_grid_dim_y; d.dim_z = voxel_grid_dim_z;
+  d.origin_x = voxel_grid_origin_x; d.origin_y = voxel_grid_origin_y; d.origin_z = voxel_grid_origin_z;
+  d.voxel_size = voxel_size; d.trunc_margin = voxel_size;
+  d.im_width = 1; d.im_height = 1;
+  d.cull_level = -1;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  d.device = dev;
+  tsdf_volume* v = nullptr;
+  int rc = tsdf_create(&d, &v);
+  if (rc) return rc;
+  int64_t n = 0;
+  std::vector<float> pts;
+  rc = tsdf_upload(v, voxel_grid_TSDF, voxel_grid_weight);
+  if (!rc) rc = tsdf_extract_surface(v, tsdf_thresh, weight_thresh, &n);
+  if (!rc) {
+    pts.resize((size_t)n * 3);
+    rc = tsdf_copy_surface(v, pts.data(), n);
+  }
+  tsdf_destroy(v);
+  if (rc) return rc;
+  return tsdf_write_ply(file_name, pts.data(), n);
+}
+
+int tsdf_selftest_rounding(int32_t device, int64_t* mismatches) {
+  if (!mismatches) return set_err(TSDF_ERR_ARG, "mismatches is NULL");
+  CK(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc(&d, sizeof *d));
+  CK(cudaMemset(d, 0, sizeof *d));
+  cudaError_t e = tsdf::launch_selftest_rounding(d, 0);
+  unsigned long long h = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CK(e);
+  *mismatches = (int64_t)h;
+  return TSDF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,551 @@
+// tsdf_kernels.cu -- hand-written sm_100a kernels of the TSDF fusion engine.
+//
+// Replaces (reference paths relative to the reference repository root):
+//   depth-fusion/demo.cu:18-68    Integrate                       -> integrate_kernel
+//   depth-fusion/demo.cu:131-145  host-side init + upload         -> fill_kernel
+//   depth-fusion/utils.hpp:82-84  ReadDepth's mm -> m conversion  -> depth_from_u16_kernel
+//   depth-fusion/utils.hpp:20-53  surface scan (count, emit)      -> extract_count/scan/emit kernels
+//
+// Numerical contract: every arithmetic step of demo.cu:30-66 is issued with an explicit
+// round-to-nearest intrinsic (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn), so nvcc can
+// never contract a multiply-add and the result is the "--fmad=false" evaluation of the reference
+// regardless of compiler flags.  The only re-arrangements are bit-exact ones: hoisting of
+// products/sums that do not depend on the inner index, powf(q,2) == q*q, skipping divisions
+// whose result is known exactly, and culling voxels that provably fail the reference's own
+// early-outs (demo.cu:43-49).
+#include "tsdf_kernels.h"
+
+namespace tsdf {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Pixel rounding.  demo.cu:46-49 computes `int p = roundf(v)` and keeps 0 <= p < size.
+// roundf(v) in [0, size)  <=>  v > -0.5 and trunc(v (+rz) 0.5) < size: adding 0.5 with
+// round-toward-zero never crosses an integer that v + 0.5 does not reach exactly, so truncation
+// of the sum is round-half-away-from-zero for v >= 0; v in (-0.5, 0) rounds to -0 -> pixel 0.
+// NaN fails the first comparison, +inf the second.  Verified over all 2^32 bit patterns by
+// selftest_rounding_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool round_pixel(float v, float size_f, int& pix) {
+  float s = __fadd_rz(v, 0.5f);
+  pix = __float2int_rz(s);
+  return (v > -0.5f) && (s < size_f);
+}
+
+struct Intrinsics {
+  float fx, fy, cx, cy;
+};
+
+// demo.cu:43-62 for one voxel whose camera-frame coordinates are already known.
+// Returns true when the voxel is to be updated with `dist`.
+__device__ __forceinline__ bool voxel_observation(float cam_x, float cam_y, float cam_z, const Intrinsics& K,
+                                                  const float* __restrict__ depth, int im_w, float im_wf,
+                                                  float im_hf, float trunc_margin, bool trunc_positive,
+                                                  float& dist) {
+  if (cam_z <= 0.0f) return false;                                   // demo.cu:43
+  const float qx = __fdiv_rn(cam_x, cam_z);
+  const float qy = __fdiv_rn(cam_y, cam_z);
+  const float u = __fadd_rn(__fmul_rn(K.fx, qx), K.cx);             // demo.cu:46
+  const float v = __fadd_rn(__fmul_rn(K.fy, qy), K.cy);             // demo.cu:47
+  int px, py;
+  const bool in_x = round_pixel(u, im_wf, px);
+  const bool in_y = round_pixel(v, im_hf, py);
+  if (!(in_x && in_y)) return false;                                 // demo.cu:48
+  const float d = __ldg(depth + (py * im_w + px));                   // demo.cu:51
+  if (d <= 0.0f || d > 6.0f) return false;                           // demo.cu:53
+  // demo.cu:56: (d - z) * sqrtf((1 + qx^2) + qy^2)
+  const float ray = __fsqrt_rn(__fadd_rn(__fadd_rn(1.0f, __fmul_rn(qx, qx)), __fmul_rn(qy, qy)));
+  const float diff = __fmul_rn(__fsub_rn(d, cam_z), ray);
+  if (diff <= -trunc_margin) return false;                           // demo.cu:57
+  // demo.cu:62: fmin(1, diff / trunc).  diff >= trunc > 0 implies RN(diff/trunc) >= 1 exactly.
+  if (trunc_positive && diff >= trunc_margin)
+    dist = 1.0f;
+  else
+    dist = fminf(1.0f, __fdiv_rn(diff, trunc_margin));
+  return true;
+}
+
+// demo.cu:63-66.  (t*w + 1)/(w + 1) with t == 1 is exactly 1 (numerator and denominator are
+// the same rounded sum), so the division is skipped for untouched free-space voxels.
+__device__ __forceinline__ void voxel_update(float& t, float& w, float dist) {
+  const float w_new = __fadd_rn(w, 1.0f);
+  if (!(dist == 1.0f && t == 1.0f)) t = __fdiv_rn(__fadd_rn(__fmul_rn(t, w), dist), w_new);
+  w = w_new;
+}
+
+template <int VEC>
+struct Row;
+template <>
+struct Row<4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 q = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
+};
+template <>
+struct Row<1> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = __ldcs(p); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { __stcs(p, v[0]); }
+};
+
+// Conservative frustum test on camera-frame points (any rounding; the margins absorb it).
+// A set of points whose convex hull is to be culled must ALL satisfy one of the five
+// half-space conditions; each condition is linear in position, so testing the hull's corners
+// covers every voxel inside it.
+struct CullAccum {
+  bool behind, left, right, top, bottom;
+  __device__ __forceinline__ CullAccum() : behind(true), left(true), right(true), top(true), bottom(true) {}
+  __device__ __forceinline__ void add(float cx, float cy, float cz, const IntegrateParams& P) {
+    // cam_z <= 0 for every voxel (demo.cu:43)
+    behind = behind && (cz < -P.cull_z);
+    // u = fx*cx/cz + cx0 < -2.5 (left) or > im_w + 1.5 (right) for every voxel with cam_z > 0
+    left   = left   && (fmaf(P.fx, cx, (P.cx + 2.5f) * cz) < -P.cull_gx);
+    right  = right  && (fmaf(P.fx, cx, (P.cx - (float)P.im_w - 1.5f) * cz) > P.cull_gx);
+    top    = top    && (fmaf(P.fy, cy, (P.cy + 2.5f) * cz) < -P.cull_gy);
+    bottom = bottom && (fmaf(P.fy, cy, (P.cy - (float)P.im_h - 1.5f) * cz) > P.cull_gy);
+  }
+  __device__ __forceinline__ bool culled() const { return behind || left || right || top || bottom; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// integrate_kernel: K frames fused per pass, each voxel's TSDF/weight held in registers.
+//
+// Thread -> voxels: one thread owns a patch of VEC consecutive x  x  ZT consecutive z voxels at
+// one y (VEC = 4: one float4 per plane).  A block of 256 threads is 2^lx_shift threads along x
+// by 256 >> lx_shift rows of y; blockIdx = (x tile, y tile, z group).  Lanes of a warp are
+// consecutive along x, so every TSDF/weight access is a fully coalesced 128-bit access.
+//
+// For a frame, the camera coordinates of voxel (j, k) of the patch are
+//   cam = ((M0*t0[j] + M4*t1) + M8*t2[k])    (demo.cu:39-41, left-to-right)
+// so the x/y part is formed once per (j) and the z product once per (k): 3 adds per voxel.
+//
+// TSDF/weight are loaded lazily -- only when some voxel of the warp is actually observed by one
+// of the K frames -- and stored only for planes that changed, so untouched parts of the volume
+// cost no HBM traffic at all.
+// ------------------------------------------------------------------------------------------------
+template <int VEC, int ZT, bool DEVPOSE>
+__global__ void __launch_bounds__(kBlockThreads, 2)
+integrate_kernel(const __grid_constant__ IntegrateParams P, const float* __restrict__ d_cam_K,
+                 const float* __restrict__ d_cam2base) {
+  __shared__ unsigned s_frame_mask;
+
+  const int lx_mask = (1 << P.lx_shift) - 1;
+  const int lx = threadIdx.x & lx_mask;
+  const int ly = threadIdx.x >> P.lx_shift;
+  const int rows_per_block = kBlockThreads >> P.lx_shift;
+  const int xu = (blockIdx.x << P.lx_shift) + lx;
+  const int y = blockIdx.y * rows_per_block + ly;
+  const int zl0 = blockIdx.z * ZT;
+  const bool active = (xu < P.nx_units) && (y < P.dim_y);
+  const int zcount = min(ZT, P.nz - zl0);
+
+  Intrinsics K;
+  FramePose dev_pose;
+  if (DEVPOSE) {
+    K.fx = __ldg(d_cam_K + 0); K.cx = __ldg(d_cam_K + 2); K.fy = __ldg(d_cam_K + 4); K.cy = __ldg(d_cam_K + 5);
+    dev_pose.m0 = __ldg(d_cam2base + 0); dev_pose.m1 = __ldg(d_cam2base + 1); dev_pose.m2 = __ldg(d_cam2base + 2);
+    dev_pose.m4 = __ldg(d_cam2base + 4); dev_pose.m5 = __ldg(d_cam2base + 5); dev_pose.m6 = __ldg(d_cam2base + 6);
+    dev_pose.m8 = __ldg(d_cam2base + 8); dev_pose.m9 = __ldg(d_cam2base + 9); dev_pose.m10 = __ldg(d_cam2base + 10);
+    dev_pose.tx = __ldg(d_cam2base + 3); dev_pose.ty = __ldg(d_cam2base + 7); dev_pose.tz = __ldg(d_cam2base + 11);
+  } else {
+    K.fx = P.fx; K.fy = P.fy; K.cx = P.cx; K.cy = P.cy;
+  }
+
+  // ---- per-tile frame mask: frames whose frustum cannot touch this tile are never looked at ----
+  unsigned frame_mask = (P.n_frames >= 32) ? 0xffffffffu : ((1u << P.n_frames) - 1u);
+  if (!DEVPOSE && P.cull_level >= 2) {
+    if (threadIdx.x < 32) {
+      bool keep = false;
+      const int f = threadIdx.x;
+      if (f < P.n_frames) {
+        const FramePose& ps = P.pose[f];
+        const int x_lo = (blockIdx.x << P.lx_shift) * VEC;
+        const int x_hi = min(P.dim_x - 1, x_lo + ((VEC << P.lx_shift) - 1));
+        const int y_lo = blockIdx.y * rows_per_block;
+        const int y_hi = min(P.dim_y - 1, y_lo + rows_per_block - 1);
+        const int z_lo = P.z_begin + zl0;
+        const int z_hi = z_lo + ZT - 1;
+        CullAccum acc;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float bx = fmaf((float)((c & 1) ? x_hi : x_lo), P.voxel_size, P.ox) - ps.tx;
+          const float by = fmaf((float)((c & 2) ? y_hi : y_lo), P.voxel_size, P.oy) - ps.ty;
+          const float bz = fmaf((float)((c & 4) ? z_hi : z_lo), P.voxel_size, P.oz) - ps.tz;
+          acc.add(fmaf(ps.m0, bx, fmaf(ps.m4, by, ps.m8 * bz)), fmaf(ps.m1, bx, fmaf(ps.m5, by, ps.m9 * bz)),
+                  fmaf(ps.m2, bx, fmaf(ps.m6, by, ps.m10 * bz)), P);
+        }
+        keep = !acc.culled();
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (threadIdx.x == 0) s_frame_mask = m;
+    }
+    __syncthreads();
+    frame_mask = s_frame_mask;
+  }
+  if (frame_mask == 0u) return;  // block-uniform
+
+  // ---- voxel-centre coordinates (demo.cu:30-32), always from the GLOBAL index ----
+  float base_x[VEC], base_z[ZT];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) base_x[j] = __fadd_rn(P.ox, __fmul_rn((float)(xu * VEC + j), P.voxel_size));
+  const float base_y = __fadd_rn(P.oy, __fmul_rn((float)y, P.voxel_size));
+#pragma unroll
+  for (int k = 0; k < ZT; ++k)
+    base_z[k] = __fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size));
+
+  // voxels of the patch that exist (x tail when dim_x % VEC != 0 is impossible: VEC divides dim_x)
+  unsigned exist_mask = 0;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < ZT; ++k)
+      if (k < zcount) exist_mask |= ((1u << VEC) - 1u) << (k * VEC);
+  }
+
+  const int64_t plane = (int64_t)P.dim_y * P.dim_x;
+  const int64_t idx0 = (int64_t)zl0 * plane + (int64_t)y * P.dim_x + (int64_t)xu * VEC;
+
+  float T[ZT][VEC], W[ZT][VEC];
+  bool loaded = false;     // warp-uniform
+  unsigned dirty = 0;      // bit k*VEC+j: voxel changed
+  const float im_wf = (float)P.im_w, im_hf = (float)P.im_h;
+  const bool trunc_positive = P.trunc_margin > 0.0f;
+
+  for (unsigned fm = frame_mask; fm != 0u; fm &= fm - 1u) {
+    const int f = __ffs(fm) - 1;
+    const FramePose& ps = DEVPOSE ? dev_pose : P.pose[f];
+    const float* __restrict__ depth = P.depth + (int64_t)f * P.frame_stride;
+
+    // (M0*t0 + M4*t1) per x, M8*t2 per z  -- demo.cu:35-41
+    float sx[VEC], sy[VEC], sz[VEC], zx[ZT], zy[ZT], zz[ZT];
+    {
+      const float t1 = __fsub_rn(base_y, ps.ty);
+      const float yx = __fmul_rn(ps.m4, t1), yy = __fmul_rn(ps.m5, t1), yz = __fmul_rn(ps.m6, t1);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float t0 = __fsub_rn(base_x[j], ps.tx);
+        sx[j] = __fadd_rn(__fmul_rn(ps.m0, t0), yx);
+        sy[j] = __fadd_rn(__fmul_rn(ps.m1, t0), yy);
+        sz[j] = __fadd_rn(__fmul_rn(ps.m2, t0), yz);
+      }
+#pragma unroll
+      for (int k = 0; k < ZT; ++k) {
+        const float t2 = __fsub_rn(base_z[k], ps.tz);
+        zx[k] = __fmul_rn(ps.m8, t2);
+        zy[k] = __fmul_rn(ps.m9, t2);
+        zz[k] = __fmul_rn(ps.m10, t2);
+      }
+    }
+
+    bool skip = !active;
+    if (P.cull_level >= 1 && !skip) {
+      // corners of the thread's x-z patch (y is fixed)
+      CullAccum acc;
+      acc.add(__fadd_rn(sx[0], zx[0]), __fadd_rn(sy[0], zy[0]), __fadd_rn(sz[0], zz[0]), P);
+      acc.add(__fadd_rn(sx[VEC - 1], zx[0]), __fadd_rn(sy[VEC - 1], zy[0]), __fadd_rn(sz[VEC - 1], zz[0]), P);
+      acc.add(__fadd_rn(sx[0], zx[ZT - 1]), __fadd_rn(sy[0], zy[ZT - 1]), __fadd_rn(sz[0], zz[ZT - 1]), P);
+      acc.add(__fadd_rn(sx[VEC - 1], zx[ZT - 1]), __fadd_rn(sy[VEC - 1], zy[ZT - 1]),
+              __fadd_rn(sz[VEC - 1], zz[ZT - 1]), P);
+      skip = acc.culled();
+    }
+    if (__all_sync(0xffffffffu, skip)) continue;  // warp-uniform
+
+#pragma unroll
+    for (int k = 0; k < ZT; ++k) {
+      float dist[VEC];
+      unsigned hit = 0;
+      if (!skip) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float cam_x = __fadd_rn(sx[j], zx[k]);
+          const float cam_y = __fadd_rn(sy[j], zy[k]);
+          const float cam_z = __fadd_rn(sz[j], zz[k]);
+          if (voxel_observation(cam_x, cam_y, cam_z, K, depth, P.im_w, im_wf, im_hf, P.trunc_margin,
+                                trunc_positive, dist[j]))
+            hit |= 1u << j;
+        }
+        hit &= exist_mask >> (k * VEC);
+      }
+      if (__any_sync(0xffffffffu, hit != 0u)) {
+        if (!loaded) {
+          loaded = true;
+#pragma unroll
+          for (int kk = 0; kk < ZT; ++kk)
+            if (active && kk < zcount) {
+              Row<VEC>::load(P.tsdf + idx0 + kk * plane, T[kk]);
+              Row<VEC>::load(P.weight + idx0 + kk * plane, W[kk]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (hit & (1u << j)) voxel_update(T[k][j], W[k][j], dist[j]);
+        dirty |= hit << (k * VEC);
+      }
+    }
+  }
+
+  // ---- store the planes that changed (warp-uniform decision -> full coalesced lines) ----
+#pragma unroll
+  for (int k = 0; k < ZT; ++k) {
+    const unsigned plane_bits = ((1u << VEC) - 1u) << (k * VEC);
+    if (__any_sync(0xffffffffu, (dirty & plane_bits) != 0u)) {
+      if (active && k < zcount) {
+        Row<VEC>::store(P.tsdf + idx0 + k * plane, T[k]);
+        Row<VEC>::store(P.weight + idx0 + k * plane, W[k]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fill: TSDF <- 1.0f, weight <- 0 (demo.cu:131-135) directly in HBM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ tsdf, float* __restrict__ weight, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    __stcs(reinterpret_cast<float4*>(tsdf) + i, one);
+    __stcs(reinterpret_cast<float4*>(weight) + i, zero);
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    tsdf[i] = 1.f;
+    weight[i] = 0.f;
+  }
+}
+
+// utils.hpp:82-84: (float)mm / 1000.0f, then > 6.0f -> 0.
+__global__ void __launch_bounds__(256) depth_from_u16_kernel(const uint16_t* __restrict__ mm,
+                                                             float* __restrict__ depth, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float d = __fdiv_rn((float)mm[i], 1000.0f);
+    if (d > 6.0f) d = 0.0f;
+    depth[i] = d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Surface extraction (utils.hpp:20-53) as an order-preserving stream compaction:
+//   count : per-tile number of surface voxels (warp ballot + popc)
+//   scan  : exclusive prefix sum of the tile counts (single block, 64-bit)
+//   emit  : per-tile re-evaluation, rank = tile offset + warp prefix + popc(ballot & lanes below)
+// A tile is kExtractTile consecutive voxels; in round r thread t looks at voxel
+// tile*4096 + r*256 + t, so ranks ascend with the linear voxel index exactly like the
+// reference's serial scan.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_surface(const ExtractParams& P, int64_t i) {
+  // utils.hpp:22 / :39: std::abs(tsdf) < tsdf_thresh && weight > weight_thresh
+  return (i < P.n) && (fabsf(__ldcs(P.tsdf + i)) < P.tsdf_thresh) && (__ldcs(P.weight + i) > P.weight_thresh);
+}
+
+constexpr int kExtractRounds = kExtractTile / kBlockThreads;  // 16
+
+__global__ void __launch_bounds__(kBlockThreads)
+extract_count_kernel(const __grid_constant__ ExtractParams P, unsigned long long* __restrict__ tile_counts,
+                     int64_t n_tiles) {
+  __shared__ unsigned s_warp[kBlockThreads / 32];
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kExtractTile + threadIdx.x;
+    unsigned cnt = 0;
+#pragma unroll
+    for (int r = 0; r < kExtractRounds; ++r) cnt += is_surface(P, base + r * kBlockThreads) ? 1u : 0u;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned total = 0;
+#pragma unroll
+      for (int w = 0; w < kBlockThreads / 32; ++w) total += s_warp[w];
+      tile_counts[tile] = total;
+    }
+    __syncthreads();
+  }
+}
+
+// In-place exclusive scan of tile_counts[0..n_tiles) by one block; *total receives the sum
+// (the engine points it at tile_counts[n_tiles], giving emit an n_tiles + 1 offset table).
+__global__ void __launch_bounds__(1024)
+extract_scan_kernel(unsigned long long* __restrict__ tile_counts, int64_t n_tiles, unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long s_part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (n_tiles + 1023) / 1024;
+  const int64_t lo = min(n_tiles, (int64_t)t * per), hi = min(n_tiles, lo + per);
+  unsigned long long sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += tile_counts[i];
+  s_part[t] = sum;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the 1024 partial sums
+  for (int off = 1; off < 1024; off <<= 1) {
+    unsigned long long v = (t >= off) ? s_part[t - off] : 0ull;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  unsigned long long run = (t == 0) ? 0ull : s_part[t - 1];
+  for (int64_t i = lo; i < hi; ++i) {
+    const unsigned long long c = tile_counts[i];
+    tile_counts[i] = run;
+    run += c;
+  }
+  if (t == 1023) *total = s_part[1023];
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+extract_emit_kernel(const __grid_constant__ ExtractParams P, const unsigned long long* __restrict__ tile_offsets,
+                    int64_t n_tiles, float* __restrict__ xyz) {
+  __shared__ unsigned s_cnt[kExtractRounds][kBlockThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t plane = (int64_t)P.dim_x * P.dim_y;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // tiles with no surface voxel (the vast majority) are skipped without touching the volume;
+    // tile_offsets has n_tiles + 1 entries, the last one being the total
+    const unsigned long long tile_base = tile_offsets[tile];
+    if (tile_offsets[tile + 1] == tile_base) continue;  // block-uniform
+    const int64_t base = tile * kExtractTile + threadIdx.x;
+    unsigned flags = 0;
+    unsigned my_rank[kExtractRounds];
+#pragma unroll
+    for (int r = 0; r < kExtractRounds; ++r) {
+      const bool s = is_surface(P, base + r * kBlockThreads);
+      const unsigned b = __ballot_sync(0xffffffffu, s);
+      if (s) flags |= 1u << r;
+      my_rank[r] = __popc(b & ((1u << lane) - 1u));
+      if (lane == 0) s_cnt[r][warp] = __popc(b);
+    }
+    __syncthreads();
+    if (flags != 0u) {
+      // prefix over (round, warp) pairs that precede this thread's (r, warp)
+      unsigned run = 0;
+#pragma unroll
+      for (int r = 0; r < kExtractRounds; ++r) {
+        unsigned before = 0, round_total = 0;
+#pragma unroll
+        for (int w = 0; w < kBlockThreads / 32; ++w) {
+          const unsigned c = s_cnt[r][w];
+          before += (w < warp) ? c : 0u;
+          round_total += c;
+        }
+        if (flags & (1u << r)) {
+          const int64_t i = base + r * kBlockThreads;
+          // utils.hpp:42-49: linear index -> (x, y, z) -> origin + (float)idx * voxel_size
+          const int64_t z = i / plane;
+          const int64_t rem = i - z * plane;
+          const int yy = (int)(rem / P.dim_x);
+          const int xx = (int)(rem - (int64_t)yy * P.dim_x);
+          float* out = xyz + 3ull * (tile_base + run + before + my_rank[r]);
+          out[0] = __fadd_rn(P.ox, __fmul_rn((float)xx, P.voxel_size));
+          out[1] = __fadd_rn(P.oy, __fmul_rn((float)yy, P.voxel_size));
+          out[2] = __fadd_rn(P.oz, __fmul_rn((float)(z + P.z_begin), P.voxel_size));
+        }
+        run += round_total;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// All 2^32 float bit patterns: round_pixel() vs roundf() + the reference's bounds test.
+__global__ void __launch_bounds__(256) selftest_rounding_kernel(unsigned long long* __restrict__ mismatches) {
+  const float sizes[3] = {640.0f, 480.0f, 1.0f};
+  unsigned long long bad = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32); b += stride) {
+    const float v = __uint_as_float((unsigned)b);
+    const float r = roundf(v);
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const bool ref_in = (r >= 0.0f) && (r < sizes[s]);
+      int pix;
+      const bool in = round_pixel(v, sizes[s], pix);
+      if (in != ref_in || (in && pix != (int)r)) ++bad;
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+int ilog2(int v) {
+  int s = 0;
+  while ((1 << (s + 1)) <= v) ++s;
+  return s;
+}
+
+template <int VEC, int ZT, bool DEVPOSE>
+cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float* d_pose, cudaStream_t s) {
+  p.nx_units = p.dim_x / VEC;
+  // threads along x: the power of two in {32, 16, 8} that wastes the fewest lanes
+  int best_lx = 32;
+  int64_t best_waste = -1;
+  for (int lx = 32; lx >= 8; lx >>= 1) {
+    const int64_t covered = (int64_t)((p.nx_units + lx - 1) / lx) * lx;
+    const int64_t waste = covered - p.nx_units;
+    if (best_waste < 0 || waste < best_waste) { best_waste = waste; best_lx = lx; }
+  }
+  p.lx_shift = ilog2(best_lx);
+  const int rows = kBlockThreads / best_lx;
+  dim3 grid((unsigned)((p.nx_units + best_lx - 1) / best_lx), (unsigned)((p.dim_y + rows - 1) / rows),
+            (unsigned)((p.nz + ZT - 1) / ZT));
+  if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
+  integrate_kernel<VEC, ZT, DEVPOSE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
+  if (p.n_frames < 1 || p.n_frames > kMaxBatch) return cudaErrorInvalidValue;
+  if (p.dim_x % 4 == 0) return launch_integrate_t<4, 4, false>(p, nullptr, nullptr, s);
+  return launch_integrate_t<1, 4, false>(p, nullptr, nullptr, s);
+}
+
+cudaError_t launch_integrate_devpose(IntegrateParams p, const float* d_cam_K, const float* d_cam2base,
+                                     cudaStream_t s) {
+  p.n_frames = 1;
+  p.cull_level = 0;  // pose unknown on the host: no margins can be derived
+  const bool vec4 = (p.dim_x % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.tsdf) & 15u) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(p.weight) & 15u) == 0);
+  if (vec4) return launch_integrate_t<4, 4, true>(p, d_cam_K, d_cam2base, s);
+  return launch_integrate_t<1, 4, true>(p, d_cam_K, d_cam2base, s);
+}
+
+cudaError_t launch_fill(float* tsdf, float* weight, int64_t n, cudaStream_t s) {
+  const int blocks = 148 * 8;
+  fill_kernel<<<blocks, 256, 0, s>>>(tsdf, weight, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_depth_from_u16(const uint16_t* mm, float* depth, int64_t n, cudaStream_t s) {
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  depth_from_u16_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(mm, depth, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_extract_count(const ExtractParams& p, unsigned long long* tile_counts, int64_t n_tiles,
+                                 cudaStream_t s) {
+  const int blocks = (int)(n_tiles < 148 * 16 ? n_tiles : 148 * 16);
+  extract_count_kernel<<<blocks > 0 ? blocks : 1, kBlockThreads, 0, s>>>(p, tile_counts, n_tiles);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_extract_scan(unsigned long long* tile_counts, int64_t n_tiles, unsigned long long* total,
+                                cudaStream_t s) {
+  extract_scan_kernel<<<1, 1024, 0, s>>>(tile_counts, n_tiles, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_extract_emit(const ExtractParams& p, const unsigned long long* tile_offsets, int64_t n_tiles,
+                                float* xyz, cudaStream_t s) {
+  const int blocks = (int)(n_tiles < 148 * 16 ? n_tiles : 148 * 16);
+  extract_emit_kernel<<<blocks > 0 ? blocks : 1, kBlockThreads, 0, s>>>(p, tile_offsets, n_tiles, xyz);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_selftest_rounding(unsigned long long* mismatches, cudaStream_t s) {
+  selftest_rounding_kernel<<<148 * 16, 256, 0, s>>>(mismatches);
+  return cudaGetLastError();
+}
+
+}  // namespace tsdf

@@ -1,0 +1,66 @@
+// tsdf_kernels.h -- launch interface between the engine (tsdf_engine.cu) and the sm_100a kernels
+// (tsdf_kernels.cu).  Internal to the library; the public surface is include/tsdf_fusion.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tsdf {
+
+constexpr int kMaxBatch = 32;    // == TSDF_MAX_BATCH
+constexpr int kBlockThreads = 256;
+
+// The 12 entries of a row-major 4x4 cam2base that demo.cu:35-41 reads, grouped by the camera
+// axis they feed: cam_x = (m0*t0 + m4*t1) + m8*t2, cam_y = (m1*t0 + m5*t1) + m9*t2, ...
+struct FramePose {
+  float m0, m1, m2;    // multiply t0 = base_x - tx
+  float m4, m5, m6;    // multiply t1 = base_y - ty
+  float m8, m9, m10;   // multiply t2 = base_z - tz
+  float tx, ty, tz;    // cam2base[3], [7], [11]
+};
+
+struct IntegrateParams {
+  float* tsdf;           // slab, x fastest
+  float* weight;
+  const float* depth;    // frame 0 of this batch; frame f at depth + f * frame_stride
+  int64_t frame_stride;  // im_height * im_width
+  int dim_x, dim_y;      // grid row length / rows per plane
+  int nz;                // planes in the slab
+  int z_begin;           // global index of the slab's first plane
+  int nx_units;          // ceil(dim_x / VEC)
+  int lx_shift;          // log2(threads of a block laid along x)
+  float ox, oy, oz, voxel_size, trunc_margin;
+  float fx, fy, cx, cy;  // cam_K[0], [4], [2], [5]
+  int im_w, im_h;
+  int n_frames;          // 1..kMaxBatch
+  int cull_level;        // 0 none, 1 per-thread frustum cull, 2 + per-tile frame mask
+  float cull_gx, cull_gy, cull_z;  // conservative margins (see make_cull_margins)
+  FramePose pose[kMaxBatch];
+};
+
+struct ExtractParams {
+  const float* tsdf;
+  const float* weight;
+  int64_t n;             // voxels in the slab
+  int dim_x, dim_y;
+  int z_begin;
+  float ox, oy, oz, voxel_size;
+  float tsdf_thresh, weight_thresh;
+};
+
+constexpr int kExtractTile = 4096;  // voxels per extraction tile (256 threads x 16)
+
+cudaError_t launch_fill(float* tsdf, float* weight, int64_t n, cudaStream_t s);
+cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s);
+// Pose and intrinsics read from DEVICE memory (reference-style Integrate argument list).
+cudaError_t launch_integrate_devpose(IntegrateParams p, const float* d_cam_K, const float* d_cam2base,
+                                     cudaStream_t s);
+cudaError_t launch_depth_from_u16(const uint16_t* mm, float* depth, int64_t n, cudaStream_t s);
+cudaError_t launch_extract_count(const ExtractParams& p, unsigned long long* tile_counts, int64_t n_tiles,
+                                 cudaStream_t s);
+cudaError_t launch_extract_scan(unsigned long long* tile_counts, int64_t n_tiles, unsigned long long* total,
+                                cudaStream_t s);
+cudaError_t launch_extract_emit(const ExtractParams& p, const unsigned long long* tile_offsets, int64_t n_tiles,
+                                float* xyz, cudaStream_t s);
+cudaError_t launch_selftest_rounding(unsigned long long* mismatches, cudaStream_t s);
+
+}  // namespace tsdf

@@ -1,0 +1,159 @@
+/*
+ * include/tsdf_fusion.h -- C ABI of the B200-native multi-frame TSDF fusion engine.
+ *
+ * Drop-in boundary for the hot path of andyzeng/3dmatch-toolbox `depth-fusion/`
+ * (reference paths below are relative to the reference repository root):
+ *
+ *   depth-fusion/demo.cu:18-68     __global__ Integrate            -> tsdf_integrate*, tsdf_Integrate
+ *   depth-fusion/demo.cu:131-153   volume init + upload            -> tsdf_create / tsdf_reset
+ *   depth-fusion/demo.cu:156-183   per-frame staging + launch loop -> tsdf_integrate_batch
+ *   depth-fusion/demo.cu:186-188   volume download                 -> tsdf_download
+ *   depth-fusion/utils.hpp:14-56   SaveVoxelGrid2SurfacePointCloud -> tsdf_extract_surface + tsdf_write_ply,
+ *                                                                     tsdf_SaveVoxelGrid2SurfacePointCloud
+ *   depth-fusion/demo.cu:196-213   tsdf.bin writer (commented out) -> tsdf_write_bin
+ *   depth-fusion/utils.hpp:60-70   LoadMatrixFromFile              -> tsdf_load_matrix
+ *   depth-fusion/utils.hpp:74-86   ReadDepth                       -> tsdf_read_depth_png, tsdf_depth_from_u16
+ *   depth-fusion/utils.hpp:89-109  multiply_matrix                 -> tsdf_multiply_matrix
+ *   depth-fusion/utils.hpp:112-238 invert_matrix                   -> tsdf_invert_matrix
+ *
+ * Conventions: plain pointers and sizes only; every entry point returns an int status
+ * (TSDF_OK == 0) unless stated; the library never prints and never calls exit();
+ * tsdf_last_error() returns the calling thread's last error text.  Device memory is owned
+ * by the handle (unless adopted through ext_tsdf/ext_weight); host memory is owned by the
+ * caller.  A handle is not thread-safe; distinct handles are independent.  There is NO CPU
+ * fallback: every compute entry point fails with TSDF_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Numerical contract: fp32, one IEEE round-to-nearest per source-level
+ * operation of demo.cu:30-66 (the "--fmad=false" evaluation), powf(q,2) == q*q, frames applied
+ * to every voxel in ascending frame order.  Results are independent of batching (K), of the
+ * z-slab decomposition and of the culling level.
+ */
+#ifndef TSDF_FUSION_H
+#define TSDF_FUSION_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSDF_OK            0
+#define TSDF_ERR_ARG       1 /* invalid argument */
+#define TSDF_ERR_CUDA      2 /* CUDA runtime error (see tsdf_last_error) */
+#define TSDF_ERR_IO        3 /* file could not be opened / read / written */
+#define TSDF_ERR_FORMAT    4 /* file content not in the expected format */
+#define TSDF_ERR_STATE     5 /* call sequence error (e.g. copy_surface before extract_surface) */
+
+#define TSDF_MAX_BATCH     32 /* frames fused per pass over the volume (K) */
+
+typedef struct tsdf_volume tsdf_volume; /* opaque engine handle */
+
+typedef struct tsdf_volume_desc {
+  int64_t dim_x, dim_y, dim_z;          /* GLOBAL grid dimensions, x fastest (demo.cu:97-99, :61) */
+  int64_t z_begin, z_end;               /* z-planes held by this handle; 0,0 or 0,dim_z = whole grid */
+  float origin_x, origin_y, origin_z;   /* grid origin in base-frame camera coordinates (demo.cu:92-94) */
+  float voxel_size;                     /* demo.cu:95 */
+  float trunc_margin;                   /* demo.cu:96 */
+  int32_t im_width, im_height;          /* depth image size (demo.cu:87-88) */
+  float cam_K[9];                       /* row-major 3x3 intrinsics (demo.cu:116-117) */
+  int32_t device;                       /* CUDA device ordinal */
+  int32_t max_batch;                    /* K: 1..TSDF_MAX_BATCH, 0 = default */
+  int32_t cull_level;                   /* 0 none, 1 per-thread frustum cull, 2 + per-tile frame mask (default: -1 = 2) */
+  int32_t reserved0;
+  void *stream;                         /* cudaStream_t to run on; NULL = the engine creates its own */
+  float *ext_tsdf, *ext_weight;         /* optional caller-owned DEVICE slabs to adopt (NULL = engine-owned) */
+} tsdf_volume_desc;
+
+typedef struct tsdf_stats {
+  int64_t kernel_launches;              /* engine kernels launched since create / last reset_stats */
+  int64_t frames_integrated;
+  int64_t h2d_bytes, d2h_bytes;
+} tsdf_stats;
+
+/* ---- engine lifecycle ------------------------------------------------------------------------ */
+int tsdf_create(const tsdf_volume_desc *desc, tsdf_volume **out);
+void tsdf_destroy(tsdf_volume *v);
+/* TSDF <- 1.0f, weight <- 0 on the device (demo.cu:131-145 without the PCIe round trip). */
+int tsdf_reset(tsdf_volume *v);
+int tsdf_synchronize(tsdf_volume *v);
+int tsdf_get_stats(tsdf_volume *v, tsdf_stats *out);
+int tsdf_reset_stats(tsdf_volume *v);
+/* CUDA-event stopwatch on the engine's own stream (the stream the kernels are launched on). */
+int tsdf_timer_start(tsdf_volume *v);
+int tsdf_timer_stop(tsdf_volume *v, float *elapsed_ms); /* records, synchronizes, returns ms */
+
+/* ---- integration ----------------------------------------------------------------------------- */
+/* One reference launch (demo.cu:173-182).  depth: im_height*im_width floats (metres, 0 = invalid),
+ * host or device memory (detected).  cam2base: 16 host floats, row-major 4x4. */
+int tsdf_integrate(tsdf_volume *v, const float *depth, const float *cam2base);
+/* n_frames reference launches in ascending order (demo.cu:156-183).  depth_frames is
+ * [n_frames][im_height*im_width] contiguous, host (pageable or pinned) or device; cam2base is
+ * [n_frames][16] on the host.  Frames are fused K at a time with each voxel's TSDF/weight held in
+ * registers across the K frames.  Asynchronous for device input; host input is staged through
+ * pinned buffers and overlapped with the kernels; call tsdf_synchronize() to wait. */
+int tsdf_integrate_batch(tsdf_volume *v, int32_t n_frames, const float *depth_frames, const float *cam2base);
+/* Same, for depth supplied as raw uint16 millimetres (the PNG payload): converted on the device
+ * exactly as ReadDepth does (utils.hpp:82-84). */
+int tsdf_integrate_batch_u16(tsdf_volume *v, int32_t n_frames, const uint16_t *depth_mm, const float *cam2base);
+
+/* ---- results --------------------------------------------------------------------------------- */
+/* Device->host copy of the slab (demo.cu:186-187).  Either pointer may be NULL. */
+int tsdf_download(tsdf_volume *v, float *tsdf_host, float *weight_host);
+int tsdf_upload(tsdf_volume *v, const float *tsdf_host, const float *weight_host);
+/* Device pointers of the slab (x fastest, (z - z_begin) slowest). */
+int tsdf_device_ptrs(tsdf_volume *v, float **tsdf_dev, float **weight_dev);
+/* Surface extraction (utils.hpp:20-53) on the device: voxels with |tsdf| < tsdf_thresh and
+ * weight > weight_thresh, emitted as voxel-centre xyz in ascending linear index.  Points stay
+ * on the device until tsdf_copy_surface. */
+int tsdf_extract_surface(tsdf_volume *v, float tsdf_thresh, float weight_thresh, int64_t *n_points);
+int tsdf_copy_surface(tsdf_volume *v, float *xyz_host, int64_t capacity_points);
+int tsdf_surface_device_ptr(tsdf_volume *v, float **xyz_dev, int64_t *n_points);
+
+/* ---- file formats (host) --------------------------------------------------------------------- */
+/* tsdf.ply: the reference's 7-line header + little-endian float xyz (utils.hpp:26-53). */
+int tsdf_write_ply(const char *path, const float *xyz, int64_t n_points);
+/* tsdf.bin: 8-float header + dim^3 TSDF floats (demo.cu:196-213). */
+int tsdf_write_bin(const char *path, int64_t dim_x, int64_t dim_y, int64_t dim_z, float origin_x,
+                   float origin_y, float origin_z, float voxel_size, float trunc_margin,
+                   const float *tsdf_host);
+/* M*N whitespace-separated floats, row-major (utils.hpp:60-70).  Fails instead of crashing when
+ * the file is missing or short. */
+int tsdf_load_matrix(const char *path, int32_t rows, int32_t cols, float *out);
+/* 16-bit grayscale PNG (millimetres) -> float metres, > 6 m -> 0 (utils.hpp:74-86). */
+int tsdf_read_depth_png(const char *path, int32_t im_height, int32_t im_width, float *depth);
+int tsdf_read_depth_png_u16(const char *path, int32_t im_height, int32_t im_width, uint16_t *depth_mm);
+void tsdf_depth_from_u16(const uint16_t *depth_mm, int64_t n, float *depth);
+
+/* ---- pose algebra (host, reference rounding) ------------------------------------------------- */
+void tsdf_multiply_matrix(const float m1[16], const float m2[16], float m_out[16]); /* utils.hpp:89-109 */
+int tsdf_invert_matrix(const float m[16], float inv_out[16]); /* utils.hpp:112-238; 1 = ok, 0 = singular */
+
+/* ---- function-level drop-ins (same argument lists as the reference) -------------------------- */
+/* Replaces `Integrate<<<dim_z, dim_y>>>(...)` (demo.cu:18-22, :179-182): all pointers are DEVICE
+ * pointers owned by the caller; TSDF/weight are updated in place on `stream` (cudaStream_t, NULL =
+ * default stream); asynchronous like a kernel launch; the return value replaces cudaGetLastError(). */
+int tsdf_Integrate(const float *cam_K, const float *cam2base, const float *depth_im, int im_height,
+                   int im_width, int voxel_grid_dim_x, int voxel_grid_dim_y, int voxel_grid_dim_z,
+                   float voxel_grid_origin_x, float voxel_grid_origin_y, float voxel_grid_origin_z,
+                   float voxel_size, float trunc_margin, float *voxel_grid_TSDF,
+                   float *voxel_grid_weight, void *stream);
+/* Replaces SaveVoxelGrid2SurfacePointCloud (utils.hpp:14-17): HOST volume pointers; the scan runs
+ * on the device and the file is byte-identical to the reference writer's. */
+int tsdf_SaveVoxelGrid2SurfacePointCloud(const char *file_name, int voxel_grid_dim_x, int voxel_grid_dim_y,
+                                         int voxel_grid_dim_z, float voxel_size, float voxel_grid_origin_x,
+                                         float voxel_grid_origin_y, float voxel_grid_origin_z,
+                                         const float *voxel_grid_TSDF, const float *voxel_grid_weight,
+                                         float tsdf_thresh, float weight_thresh);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+const char *tsdf_last_error(void);
+const char *tsdf_version(void);
+int tsdf_device_count(int32_t *count);
+/* Device self-test of the pixel rounding helper against roundf() + the reference bounds test
+ * (demo.cu:46-49) over all 2^32 float bit patterns; *mismatches receives the count (0 expected). */
+int tsdf_selftest_rounding(int32_t device, int64_t *mismatches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDF_FUSION_H */
