@@ -229,7 +229,7 @@ class Volume:
     """A TSDF volume (or one z-slab of it) resident in the HBM of one GPU."""
 
     def __init__(self, dims, origin, voxel_size, trunc_margin, cam_K, im_size=(640, 480), z_range=None,
-                 device=0, max_batch=0, cull_level=-1, stream=0, ext_tsdf=None, ext_weight=None):
+                 device=0, max_batch=0, cull_level=-1, stream=0, ext_tsdf=None, ext_weight=None, tuning=0):
         self._lib = load_library()
         d = VolumeDesc()
         d.dim_x, d.dim_y, d.dim_z = (int(v) for v in dims)
@@ -239,6 +239,7 @@ class Volume:
         d.im_width, d.im_height = int(im_size[0]), int(im_size[1])
         d.cam_K = (C.c_float * 9)(*[float(v) for v in np.asarray(cam_K, np.float32).ravel()])
         d.device, d.max_batch, d.cull_level = int(device), int(max_batch), int(cull_level)
+        d.reserved0 = int(tuning)  # bits 0-7: kernel tuning variant, bit 8: exact path only (validation)
         d.stream = stream or None
         d.ext_tsdf = _ptr(ext_tsdf) if ext_tsdf is not None else None
         d.ext_weight = _ptr(ext_weight) if ext_weight is not None else None

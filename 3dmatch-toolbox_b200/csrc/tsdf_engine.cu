@@ -41,7 +41,7 @@ void tsdf_set_error_text(const char* text) { snprintf(g_err, sizeof g_err, "%s",
 struct tsdf_volume {
   tsdf_volume_desc d;
   int64_t nz = 0, n_vox = 0, frame_px = 0;
-  int batch = 0, cull = 2;
+  int batch = 0, cull = 2, tuning = 0;
   float* tsdf = nullptr;
   float* weight = nullptr;
   bool owns_volume = false;
@@ -111,6 +111,8 @@ void fill_params(const tsdf_volume* v, tsdf::IntegrateParams* p) {
   p->fx = v->d.cam_K[0]; p->cx = v->d.cam_K[2]; p->fy = v->d.cam_K[4]; p->cy = v->d.cam_K[5];
   p->im_w = v->d.im_width; p->im_h = v->d.im_height;
   p->cull_level = v->cull;
+  p->fast_level = (v->tuning & 0x100) ? 0 : 1;
+  p->variant = v->tuning & 0xff;
 }
 
 void pose_from_cam2base(const float* c, tsdf::FramePose* o) {
@@ -250,6 +252,7 @@ int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
   v->frame_px = (int64_t)d.im_width * d.im_height;
   v->batch = d.max_batch ? d.max_batch : 16;
   v->cull = (d.cull_level < 0 || d.cull_level > 2) ? 2 : d.cull_level;
+  v->tuning = d.reserved0;
   {
     const float ex = fmaxf(fabsf(d.origin_x), fabsf(d.origin_x + (float)d.dim_x * d.voxel_size));
     const float ey = fmaxf(fabsf(d.origin_y), fabsf(d.origin_y + (float)d.dim_y * d.voxel_size));

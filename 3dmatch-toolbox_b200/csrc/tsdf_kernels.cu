@@ -35,35 +35,84 @@ __device__ __forceinline__ bool round_pixel(float v, float size_f, int& pix) {
 
 struct Intrinsics {
   float fx, fy, cx, cy;
+  float lim_x, lim_y;  // 0.5 - pixel_round_margin(): |u' - round(u')| below this => rounding is certain
 };
 
-// demo.cu:43-62 for one voxel whose camera-frame coordinates are already known.
-// Returns true when the voxel is to be updated with `dist`.
-__device__ __forceinline__ bool voxel_observation(float cam_x, float cam_y, float cam_z, const Intrinsics& K,
-                                                  const float* __restrict__ depth, int im_w, float im_wf,
-                                                  float im_hf, float trunc_margin, bool trunc_positive,
-                                                  float& dist) {
-  if (cam_z <= 0.0f) return false;                                   // demo.cu:43
+// demo.cu:43-62 for one voxel, evaluated exactly as the reference does (one rounding per operation).
+// Returns dist (in (-1, 1]) when the voxel is to be updated, kNoObservation otherwise.  Kept out of
+// line: after the fast classification below only a few percent of the voxels come here.
+// BAND_SHORTCUT applies the +-trunc band argument of voxel_classify (2) after the exact pixel has
+// been found; with false the function is the plain restatement (validation mode).
+constexpr float kNoObservation = 2.0f;
+template <bool BAND_SHORTCUT>
+__device__ __noinline__ float voxel_observation_exact(float cam_x, float cam_y, float cam_z, float fx, float fy,
+                                                      float cx, float cy, const float* __restrict__ depth,
+                                                      int im_w, int im_h, float trunc_margin) {
+  if (cam_z <= 0.0f) return kNoObservation;                          // demo.cu:43
   const float qx = __fdiv_rn(cam_x, cam_z);
   const float qy = __fdiv_rn(cam_y, cam_z);
-  const float u = __fadd_rn(__fmul_rn(K.fx, qx), K.cx);             // demo.cu:46
-  const float v = __fadd_rn(__fmul_rn(K.fy, qy), K.cy);             // demo.cu:47
+  const float u = __fadd_rn(__fmul_rn(fx, qx), cx);                 // demo.cu:46
+  const float v = __fadd_rn(__fmul_rn(fy, qy), cy);                 // demo.cu:47
   int px, py;
-  const bool in_x = round_pixel(u, im_wf, px);
-  const bool in_y = round_pixel(v, im_hf, py);
-  if (!(in_x && in_y)) return false;                                 // demo.cu:48
+  const bool in_x = round_pixel(u, (float)im_w, px);
+  const bool in_y = round_pixel(v, (float)im_h, py);
+  if (!(in_x && in_y)) return kNoObservation;                        // demo.cu:48
   const float d = __ldg(depth + (py * im_w + px));                   // demo.cu:51
-  if (d <= 0.0f || d > 6.0f) return false;                           // demo.cu:53
+  if (d <= 0.0f || d > 6.0f) return kNoObservation;                  // demo.cu:53
+  const float e = __fsub_rn(d, cam_z);
+  if (BAND_SHORTCUT && trunc_margin > 0.0f) {
+    if (e >= trunc_margin) return 1.0f;
+    if (e <= -trunc_margin) return kNoObservation;
+  }
   // demo.cu:56: (d - z) * sqrtf((1 + qx^2) + qy^2)
   const float ray = __fsqrt_rn(__fadd_rn(__fadd_rn(1.0f, __fmul_rn(qx, qx)), __fmul_rn(qy, qy)));
-  const float diff = __fmul_rn(__fsub_rn(d, cam_z), ray);
-  if (diff <= -trunc_margin) return false;                           // demo.cu:57
-  // demo.cu:62: fmin(1, diff / trunc).  diff >= trunc > 0 implies RN(diff/trunc) >= 1 exactly.
-  if (trunc_positive && diff >= trunc_margin)
-    dist = 1.0f;
-  else
-    dist = fminf(1.0f, __fdiv_rn(diff, trunc_margin));
-  return true;
+  const float diff = __fmul_rn(e, ray);
+  if (diff <= -trunc_margin) return kNoObservation;                  // demo.cu:57
+  return fminf(1.0f, __fdiv_rn(diff, trunc_margin));                 // demo.cu:62
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast, bit-exact classification of one voxel (branch-free apart from the predicated gather).
+//
+// (1) Pixel.  u' = cam_x * (fx * rcp(cam_z)) + cx differs from the reference's
+//     u = fl(fl(fx * fl(cam_x / cam_z)) + cx) by less than pixel_round_margin() (see there), so
+//     whenever u' is further than that from every half-integer, roundf(u) == rint(u') and the two
+//     IEEE divisions are not needed.  rint() is taken with the 1.5 * 2^23 trick (no F2I): for
+//     |u'| < 2^22 the low mantissa bits of u' + 1.5*2^23 are rint(u'); for larger |u'| the
+//     difference (u' + M) - M is not within lim of u' or the integer is far outside the image.
+// (2) Distance.  ray = sqrtf(1 + qx^2 + qy^2) >= 1 exactly, hence with e = fl(d - cam_z):
+//       e >=  trunc  =>  diff = fl(e * ray) >=  trunc  =>  dist = fmin(1, diff / trunc) = 1
+//       e <= -trunc  =>  diff <= -trunc                =>  voxel skipped (demo.cu:57)
+//     and only the +-trunc band around the surface needs ray and the division.
+// Everything that is not certain is sent to voxel_observation_exact().
+// ------------------------------------------------------------------------------------------------
+constexpr float kRintMagic = 12582912.0f;  // 1.5 * 2^23
+constexpr int kRintMagicBits = 0x4B400000;
+
+__device__ __forceinline__ void voxel_classify(float cam_x, float cam_y, float cam_z, const Intrinsics& K,
+                                               const float* __restrict__ depth, int im_w, int im_h,
+                                               float trunc_margin, bool& free_space, bool& need_exact) {
+  const float r = rcp_approx(cam_z);
+  const float ua = fmaf(cam_x, r * K.fx, K.cx);
+  const float va = fmaf(cam_y, r * K.fy, K.cy);
+  const float tu = ua + kRintMagic, tv = va + kRintMagic;
+  const bool certain = (fabsf(ua - (tu - kRintMagic)) < K.lim_x) & (fabsf(va - (tv - kRintMagic)) < K.lim_y);
+  const unsigned ix = (unsigned)(__float_as_int(tu) - kRintMagicBits);
+  const unsigned iy = (unsigned)(__float_as_int(tv) - kRintMagicBits);
+  const bool pos = cam_z > 0.0f;                                   // demo.cu:43 (NaN: rejected at :48 there)
+  const bool inb = (ix < (unsigned)im_w) & (iy < (unsigned)im_h);  // demo.cu:48
+  float d = 0.0f;
+  if (pos & certain & inb) d = __ldg(depth + (iy * (unsigned)im_w + ix));  // demo.cu:51
+  const float e = __fsub_rn(d, cam_z);
+  const bool valid = (d > 0.0f) & (d <= 6.0f);                     // demo.cu:53
+  free_space = valid & (e >= trunc_margin);
+  need_exact = pos & (!certain | (valid & (e > -trunc_margin) & !(e >= trunc_margin)));
 }
 
 // demo.cu:63-66.  (t*w + 1)/(w + 1) with t == 1 is exactly 1 (numerator and denominator are
@@ -99,14 +148,14 @@ struct Row<1> {
 struct CullAccum {
   bool behind, left, right, top, bottom;
   __device__ __forceinline__ CullAccum() : behind(true), left(true), right(true), top(true), bottom(true) {}
-  __device__ __forceinline__ void add(float cx, float cy, float cz, const IntegrateParams& P) {
+  __device__ __forceinline__ void add(float cx, float cy, float cz, const IntegrateParams& P, const Intrinsics& K) {
     // cam_z <= 0 for every voxel (demo.cu:43)
     behind = behind && (cz < -P.cull_z);
     // u = fx*cx/cz + cx0 < -2.5 (left) or > im_w + 1.5 (right) for every voxel with cam_z > 0
-    left   = left   && (fmaf(P.fx, cx, (P.cx + 2.5f) * cz) < -P.cull_gx);
-    right  = right  && (fmaf(P.fx, cx, (P.cx - (float)P.im_w - 1.5f) * cz) > P.cull_gx);
-    top    = top    && (fmaf(P.fy, cy, (P.cy + 2.5f) * cz) < -P.cull_gy);
-    bottom = bottom && (fmaf(P.fy, cy, (P.cy - (float)P.im_h - 1.5f) * cz) > P.cull_gy);
+    left   = left   && (fmaf(K.fx, cx, (K.cx + 2.5f) * cz) < -P.cull_gx);
+    right  = right  && (fmaf(K.fx, cx, (K.cx - (float)P.im_w - 1.5f) * cz) > P.cull_gx);
+    top    = top    && (fmaf(K.fy, cy, (K.cy + 2.5f) * cz) < -P.cull_gy);
+    bottom = bottom && (fmaf(K.fy, cy, (K.cy - (float)P.im_h - 1.5f) * cz) > P.cull_gy);
   }
   __device__ __forceinline__ bool culled() const { return behind || left || right || top || bottom; }
 };
@@ -117,7 +166,8 @@ struct CullAccum {
 // Thread -> voxels: one thread owns a patch of VEC consecutive x  x  ZT consecutive z voxels at
 // one y (VEC = 4: one float4 per plane).  A block of 256 threads is 2^lx_shift threads along x
 // by 256 >> lx_shift rows of y; blockIdx = (x tile, y tile, z group).  Lanes of a warp are
-// consecutive along x, so every TSDF/weight access is a fully coalesced 128-bit access.
+// consecutive along x, so every TSDF/weight access is a fully coalesced 128-bit access, and the
+// ZT planes of a patch project to (nearly) the same pixels, so the depth gather hits L1.
 //
 // For a frame, the camera coordinates of voxel (j, k) of the patch are
 //   cam = ((M0*t0[j] + M4*t1) + M8*t2[k])    (demo.cu:39-41, left-to-right)
@@ -127,12 +177,10 @@ struct CullAccum {
 // of the K frames -- and stored only for planes that changed, so untouched parts of the volume
 // cost no HBM traffic at all.
 // ------------------------------------------------------------------------------------------------
-template <int VEC, int ZT, bool DEVPOSE>
-__global__ void __launch_bounds__(kBlockThreads, 2)
+template <int VEC, int ZT, bool DEVPOSE, int MINB, bool FAST>
+__global__ void __launch_bounds__(kBlockThreads, MINB)
 integrate_kernel(const __grid_constant__ IntegrateParams P, const float* __restrict__ d_cam_K,
                  const float* __restrict__ d_cam2base) {
-  __shared__ unsigned s_frame_mask;
-
   const int lx_mask = (1 << P.lx_shift) - 1;
   const int lx = threadIdx.x & lx_mask;
   const int ly = threadIdx.x >> P.lx_shift;
@@ -147,46 +195,46 @@ integrate_kernel(const __grid_constant__ IntegrateParams P, const float* __restr
   FramePose dev_pose;
   if (DEVPOSE) {
     K.fx = __ldg(d_cam_K + 0); K.cx = __ldg(d_cam_K + 2); K.fy = __ldg(d_cam_K + 4); K.cy = __ldg(d_cam_K + 5);
+    K.lim_x = 0.5f - pixel_round_margin((float)P.im_w, K.cx);
+    K.lim_y = 0.5f - pixel_round_margin((float)P.im_h, K.cy);
     dev_pose.m0 = __ldg(d_cam2base + 0); dev_pose.m1 = __ldg(d_cam2base + 1); dev_pose.m2 = __ldg(d_cam2base + 2);
     dev_pose.m4 = __ldg(d_cam2base + 4); dev_pose.m5 = __ldg(d_cam2base + 5); dev_pose.m6 = __ldg(d_cam2base + 6);
     dev_pose.m8 = __ldg(d_cam2base + 8); dev_pose.m9 = __ldg(d_cam2base + 9); dev_pose.m10 = __ldg(d_cam2base + 10);
     dev_pose.tx = __ldg(d_cam2base + 3); dev_pose.ty = __ldg(d_cam2base + 7); dev_pose.tz = __ldg(d_cam2base + 11);
   } else {
     K.fx = P.fx; K.fy = P.fy; K.cx = P.cx; K.cy = P.cy;
+    K.lim_x = P.lim_x; K.lim_y = P.lim_y;
   }
 
-  // ---- per-tile frame mask: frames whose frustum cannot touch this tile are never looked at ----
+  // ---- per-warp frame mask: lane f tests frame f against the bounding box of the warp's voxels
+  //      (2^lx_shift*VEC x 32>>lx_shift x ZT); frames whose frustum cannot touch it are never looked at
   unsigned frame_mask = (P.n_frames >= 32) ? 0xffffffffu : ((1u << P.n_frames) - 1u);
-  if (!DEVPOSE && P.cull_level >= 2) {
-    if (threadIdx.x < 32) {
-      bool keep = false;
-      const int f = threadIdx.x;
-      if (f < P.n_frames) {
-        const FramePose& ps = P.pose[f];
-        const int x_lo = (blockIdx.x << P.lx_shift) * VEC;
-        const int x_hi = min(P.dim_x - 1, x_lo + ((VEC << P.lx_shift) - 1));
-        const int y_lo = blockIdx.y * rows_per_block;
-        const int y_hi = min(P.dim_y - 1, y_lo + rows_per_block - 1);
-        const int z_lo = P.z_begin + zl0;
-        const int z_hi = z_lo + ZT - 1;
-        CullAccum acc;
+  if (!DEVPOSE && P.cull_level >= 1) {
+    bool keep = false;
+    const int f = threadIdx.x & 31;
+    if (f < P.n_frames) {
+      const FramePose& ps = P.pose[f];
+      const int rows_per_warp = 32 >> P.lx_shift;
+      const int x_lo = (blockIdx.x << P.lx_shift) * VEC;
+      const int x_hi = min(P.dim_x - 1, x_lo + ((VEC << P.lx_shift) - 1));
+      const int y_lo = blockIdx.y * rows_per_block + (threadIdx.x >> 5) * rows_per_warp;
+      const int y_hi = min(P.dim_y - 1, y_lo + rows_per_warp - 1);
+      const int z_lo = P.z_begin + zl0;
+      const int z_hi = z_lo + ZT - 1;
+      CullAccum acc;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float bx = fmaf((float)((c & 1) ? x_hi : x_lo), P.voxel_size, P.ox) - ps.tx;
-          const float by = fmaf((float)((c & 2) ? y_hi : y_lo), P.voxel_size, P.oy) - ps.ty;
-          const float bz = fmaf((float)((c & 4) ? z_hi : z_lo), P.voxel_size, P.oz) - ps.tz;
-          acc.add(fmaf(ps.m0, bx, fmaf(ps.m4, by, ps.m8 * bz)), fmaf(ps.m1, bx, fmaf(ps.m5, by, ps.m9 * bz)),
-                  fmaf(ps.m2, bx, fmaf(ps.m6, by, ps.m10 * bz)), P);
-        }
-        keep = !acc.culled();
+      for (int c = 0; c < 8; ++c) {
+        const float bx = fmaf((float)((c & 1) ? x_hi : x_lo), P.voxel_size, P.ox) - ps.tx;
+        const float by = fmaf((float)((c & 2) ? y_hi : y_lo), P.voxel_size, P.oy) - ps.ty;
+        const float bz = fmaf((float)((c & 4) ? z_hi : z_lo), P.voxel_size, P.oz) - ps.tz;
+        acc.add(fmaf(ps.m0, bx, fmaf(ps.m4, by, ps.m8 * bz)), fmaf(ps.m1, bx, fmaf(ps.m5, by, ps.m9 * bz)),
+                fmaf(ps.m2, bx, fmaf(ps.m6, by, ps.m10 * bz)), P, K);
       }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (threadIdx.x == 0) s_frame_mask = m;
+      keep = !acc.culled() && (y_lo < P.dim_y);
     }
-    __syncthreads();
-    frame_mask = s_frame_mask;
+    frame_mask = __ballot_sync(0xffffffffu, keep);
   }
-  if (frame_mask == 0u) return;  // block-uniform
+  if (frame_mask == 0u) return;  // warp-uniform
 
   // ---- voxel-centre coordinates (demo.cu:30-32), always from the GLOBAL index ----
   float base_x[VEC], base_z[ZT];
@@ -197,7 +245,7 @@ integrate_kernel(const __grid_constant__ IntegrateParams P, const float* __restr
   for (int k = 0; k < ZT; ++k)
     base_z[k] = __fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size));
 
-  // voxels of the patch that exist (x tail when dim_x % VEC != 0 is impossible: VEC divides dim_x)
+  // voxels of the patch that exist (VEC divides dim_x, so there is no x tail inside a patch)
   unsigned exist_mask = 0;
   if (active) {
 #pragma unroll
@@ -211,8 +259,7 @@ integrate_kernel(const __grid_constant__ IntegrateParams P, const float* __restr
   float T[ZT][VEC], W[ZT][VEC];
   bool loaded = false;     // warp-uniform
   unsigned dirty = 0;      // bit k*VEC+j: voxel changed
-  const float im_wf = (float)P.im_w, im_hf = (float)P.im_h;
-  const bool trunc_positive = P.trunc_margin > 0.0f;
+  constexpr bool use_fast = FAST;  // the launcher falls back to FAST = false when trunc_margin <= 0
 
   for (unsigned fm = frame_mask; fm != 0u; fm &= fm - 1u) {
     const int f = __ffs(fm) - 1;
@@ -240,32 +287,38 @@ integrate_kernel(const __grid_constant__ IntegrateParams P, const float* __restr
       }
     }
 
-    bool skip = !active;
-    if (P.cull_level >= 1 && !skip) {
-      // corners of the thread's x-z patch (y is fixed)
-      CullAccum acc;
-      acc.add(__fadd_rn(sx[0], zx[0]), __fadd_rn(sy[0], zy[0]), __fadd_rn(sz[0], zz[0]), P);
-      acc.add(__fadd_rn(sx[VEC - 1], zx[0]), __fadd_rn(sy[VEC - 1], zy[0]), __fadd_rn(sz[VEC - 1], zz[0]), P);
-      acc.add(__fadd_rn(sx[0], zx[ZT - 1]), __fadd_rn(sy[0], zy[ZT - 1]), __fadd_rn(sz[0], zz[ZT - 1]), P);
-      acc.add(__fadd_rn(sx[VEC - 1], zx[ZT - 1]), __fadd_rn(sy[VEC - 1], zy[ZT - 1]),
-              __fadd_rn(sz[VEC - 1], zz[ZT - 1]), P);
-      skip = acc.culled();
-    }
-    if (__all_sync(0xffffffffu, skip)) continue;  // warp-uniform
-
 #pragma unroll
     for (int k = 0; k < ZT; ++k) {
       float dist[VEC];
       unsigned hit = 0;
-      if (!skip) {
+      if (active) {
+        unsigned exact = 0;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          const float cam_x = __fadd_rn(sx[j], zx[k]);
-          const float cam_y = __fadd_rn(sy[j], zy[k]);
-          const float cam_z = __fadd_rn(sz[j], zz[k]);
-          if (voxel_observation(cam_x, cam_y, cam_z, K, depth, P.im_w, im_wf, im_hf, P.trunc_margin,
-                                trunc_positive, dist[j]))
-            hit |= 1u << j;
+          dist[j] = 1.0f;
+          bool free_space = false, need_exact = true;
+          if (use_fast)
+            voxel_classify(__fadd_rn(sx[j], zx[k]), __fadd_rn(sy[j], zy[k]), __fadd_rn(sz[j], zz[k]), K, depth,
+                           P.im_w, P.im_h, P.trunc_margin, free_space, need_exact);
+          hit |= (free_space ? 1u : 0u) << j;
+          exact |= (need_exact ? 1u : 0u) << j;
+        }
+        if (exact != 0u) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if (exact & (1u << j)) {
+              const float cam_x = __fadd_rn(sx[j], zx[k]), cam_y = __fadd_rn(sy[j], zy[k]),
+                          cam_z = __fadd_rn(sz[j], zz[k]);
+              const float dj = use_fast
+                  ? voxel_observation_exact<true>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy, depth, P.im_w,
+                                                  P.im_h, P.trunc_margin)
+                  : voxel_observation_exact<false>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy, depth, P.im_w,
+                                                   P.im_h, P.trunc_margin);
+              if (dj != kNoObservation) {
+                dist[j] = dj;
+                hit |= 1u << j;
+              }
+            }
         }
         hit &= exist_mask >> (k * VEC);
       }
@@ -473,9 +526,11 @@ int ilog2(int v) {
   return s;
 }
 
-template <int VEC, int ZT, bool DEVPOSE>
+template <int VEC, int ZT, bool DEVPOSE, int MINB, bool FAST = true>
 cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float* d_pose, cudaStream_t s) {
   p.nx_units = p.dim_x / VEC;
+  p.lim_x = 0.5f - pixel_round_margin((float)p.im_w, p.cx);
+  p.lim_y = 0.5f - pixel_round_margin((float)p.im_h, p.cy);
   // threads along x: the power of two in {32, 16, 8} that wastes the fewest lanes
   int best_lx = 32;
   int64_t best_waste = -1;
@@ -489,7 +544,9 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
   dim3 grid((unsigned)((p.nx_units + best_lx - 1) / best_lx), (unsigned)((p.dim_y + rows - 1) / rows),
             (unsigned)((p.nz + ZT - 1) / ZT));
   if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
-  integrate_kernel<VEC, ZT, DEVPOSE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+  if (FAST && (p.fast_level == 0 || !(p.trunc_margin > 0.0f)))
+    return launch_integrate_t<VEC, ZT, DEVPOSE, MINB, false>(p, d_K, d_pose, s);
+  integrate_kernel<VEC, ZT, DEVPOSE, MINB, FAST><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
   return cudaGetLastError();
 }
 
@@ -497,18 +554,25 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
 
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
   if (p.n_frames < 1 || p.n_frames > kMaxBatch) return cudaErrorInvalidValue;
-  if (p.dim_x % 4 == 0) return launch_integrate_t<4, 4, false>(p, nullptr, nullptr, s);
-  return launch_integrate_t<1, 4, false>(p, nullptr, nullptr, s);
+  if (p.dim_x % 4 != 0) return launch_integrate_t<1, 4, false, 3>(p, nullptr, nullptr, s);
+  switch (p.variant) {  // tuning variants (tsdf_volume_desc.reserved0); 0 is the production choice
+    case 1: return launch_integrate_t<4, 4, false, 2>(p, nullptr, nullptr, s);
+    case 2: return launch_integrate_t<4, 4, false, 4>(p, nullptr, nullptr, s);
+    case 3: return launch_integrate_t<4, 2, false, 4>(p, nullptr, nullptr, s);
+    case 4: return launch_integrate_t<4, 2, false, 5>(p, nullptr, nullptr, s);
+    default: return launch_integrate_t<4, 4, false, 3>(p, nullptr, nullptr, s);
+  }
 }
 
 cudaError_t launch_integrate_devpose(IntegrateParams p, const float* d_cam_K, const float* d_cam2base,
                                      cudaStream_t s) {
   p.n_frames = 1;
   p.cull_level = 0;  // pose unknown on the host: no margins can be derived
+  p.fast_level = 1;
   const bool vec4 = (p.dim_x % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.tsdf) & 15u) == 0) &&
                     ((reinterpret_cast<uintptr_t>(p.weight) & 15u) == 0);
-  if (vec4) return launch_integrate_t<4, 4, true>(p, d_cam_K, d_cam2base, s);
-  return launch_integrate_t<1, 4, true>(p, d_cam_K, d_cam2base, s);
+  if (vec4) return launch_integrate_t<4, 4, true, 3>(p, d_cam_K, d_cam2base, s);
+  return launch_integrate_t<1, 4, true, 3>(p, d_cam_K, d_cam2base, s);
 }
 
 cudaError_t launch_fill(float* tsdf, float* weight, int64_t n, cudaStream_t s) {

@@ -34,6 +34,9 @@ struct IntegrateParams {
   int n_frames;          // 1..kMaxBatch
   int cull_level;        // 0 none, 1 per-thread frustum cull, 2 + per-tile frame mask
   float cull_gx, cull_gy, cull_z;  // conservative margins (see make_cull_margins)
+  int fast_level;        // 0: every voxel through the exact path, 1: fast classification first
+  int variant;           // tuning variant of the kernel instantiation (0 = production)
+  float lim_x, lim_y;    // filled by the launcher: 0.5 - pixel_round_margin()
   FramePose pose[kMaxBatch];
 };
 
@@ -46,6 +49,16 @@ struct ExtractParams {
   float ox, oy, oz, voxel_size;
   float tsdf_thresh, weight_thresh;
 };
+
+// Bound on |u' - u| between the fast pixel coordinate u' = fma(cam, fx * rcp.approx(z), c0) and the
+// reference's u = fl(fl(fx * fl(cam / z)) + c0) for |u'| <= size + 1.5.  Relative errors: rcp.approx
+// <= 2^-23, every rounded product <= 2^-24, so fl(fx * fl(cam/z)) and cam * fl(fx * rcp(z)) differ by
+// at most 5 * 2^-24 * |fx cam / z| <= 2.98e-7 * (size + 1.5 + |c0|); the two final roundings add
+// 2 * 2^-24 * (size + 1.5).  The returned margin is twice that bound.
+__host__ __device__ inline float pixel_round_margin(float size, float c0) {
+  const float mag = size + 1.5f;
+  return 2.0f * (2.98e-7f * (mag + (c0 < 0.f ? -c0 : c0)) + 1.2e-7f * mag) + 1e-6f;
+}
 
 constexpr int kExtractTile = 4096;  // voxels per extraction tile (256 threads x 16)
 

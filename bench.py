@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- TSDF voxel-updates/s and HBM roofline fraction of the fusion hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1024|512|demo500]
+
+A "step" fuses the configuration's whole synthetic sequence (F frames of 640x480 depth) into the
+volume: volume re-initialisation on the device (demo.cu:131-145) plus ceil(F / batch) launches of the
+K-frame integrate kernel (demo.cu:156-183).  N > 1 (launched by torch.distributed.run, one rank per
+GPU): the volume is split into contiguous z-slabs, rank 0 renders the frames and broadcasts them over
+NCCL, every rank fuses all frames into its slab; no collective on the data path (strong scaling).
+
+`value`   : voxel-updates/s (voxels x frames / time) with the frames resident in HBM, CUDA-event
+            timed on the engine's stream, max over ranks.
+`e2e`     : the same metric through the public C-ABI call with HOST (pinned) depth buffers: H2D of
+            every frame, fusion, surface extraction and D2H of the surface points inside the timed
+            region.
+`roofline`: algorithmic bytes (16 B per voxel per pass over the volume) of the
+            integrate kernel / its measured average duration, against the measured HBM copy peak.
+`cpu_baseline`: the reference's Integrate body compiled for the host (oracle/_ref) -- or the oracle
+            port -- on a bounded z-slab / frame sample of the same workload, all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "tsdf_voxel_updates_per_sec"
+UNIT = "voxel-updates/s"
+BYTES_PER_VOXEL_PASS = 16  # TSDF + weight, read + write
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_inputs(pkg, cfg, device, rank, world, dist):
+    """Frames rendered on rank 0's GPU and broadcast over NCCL; poses via the reference's host algebra."""
+    import torch
+    synth = pkg.synth
+    F = cfg["frames"]
+    frames = list(range(F))
+    mm = torch.empty((F, 480, 640), dtype=torch.int32, device=device)
+    if rank == 0:
+        for f0 in range(0, F, 50):
+            mm[f0:f0 + 50] = synth.render_depth_mm(frames[f0:f0 + 50], device=device)
+    if world > 1:
+        dist.broadcast(mm, src=0)
+    # utils.hpp:82-84 on the device: (float)mm / 1000.0f (IEEE division), > 6 -> 0
+    depth = torch.div(mm.to(torch.float32), torch.full((1,), 1000.0, dtype=torch.float32, device=device))
+    depth = torch.where(depth > 6.0, torch.zeros_like(depth), depth).contiguous()
+    check = pkg.depth_from_u16(mm[0].cpu().numpy().astype(np.uint16))
+    if not np.array_equal(check.view(np.uint32), depth[0].cpu().numpy().view(np.uint32)):
+        raise RuntimeError("device depth conversion is not bit-identical to ReadDepth's")
+    c2w, b2w = synth.make_poses(frames)
+    poses = np.stack([pkg.cam2base_from_world(b2w, m).ravel() for m in c2w]).astype(np.float32)
+    del mm
+    torch.cuda.synchronize()  # the engine runs on its own stream
+    return depth, poses
+
+
+def slab_range(dim_z, rank, world):
+    return (dim_z * rank) // world, (dim_z * (rank + 1)) // world
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    pkg = graft.load_package()
+    synth = pkg.synth
+    cfg = dict(synth.CONFIGS[args.config])
+    if args.frames:
+        cfg["frames"] = args.frames
+    grid, F = cfg["grid"], cfg["frames"]
+    z0, z1 = slab_range(grid.dims[2], rank, world)
+    depth, poses = build_inputs(pkg, cfg, device, rank, world, dist)
+
+    vol = pkg.Volume(grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin, synth.CAM_K, z_range=(z0, z1),
+                     device=local_rank, max_batch=args.batch, cull_level=args.cull, tuning=args.tuning)
+    slab_voxels = vol.n_voxels
+    total_voxels = grid.n_voxels
+
+    def step_device():
+        vol.reset()
+        vol.integrate_batch(depth, poses)
+
+    # ---- value: inputs resident in HBM --------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    vol.reset_stats()
+    barrier()
+    vol.timer_start()
+    for _ in range(args.steps):
+        step_device()
+    ms = vol.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sum_over_ranks(vol.stats()["kernel_launches"])
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = total_voxels * F / (ms_per_step * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "ms_per_step": round(ms_per_step, 3),
+                              "config_key": args.config, "frames": F, "batch": args.batch, "cull": args.cull,
+                              "tuning": args.tuning, "clocks": clocks, "quick": True}), flush=True)
+        vol.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K-frame integrate): launches only, no reset --------------
+    vol.reset()
+    vol.synchronize()
+    vol.timer_start()
+    vol.integrate_batch(depth, poses)
+    ms_int = max_over_ranks(vol.timer_stop())
+    n_launch = -(-F // args.batch)
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes_per_launch = BYTES_PER_VOXEL_PASS * slab_voxels
+    achieved = alg_bytes_per_launch / (ms_int / n_launch * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(f"{args.config}_k{args.batch}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "kernel": "integrate_kernel<4,4>", "frames_per_launch": args.batch,
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "avg_launch_ms": round(ms_int / n_launch, 4),
+                "updates_per_sec_roofline": peak * 1e9 / BYTES_PER_VOXEL_PASS * args.batch,
+                "note": "16 B/voxel/pass amortised over K frames; the kernel loads/stores only voxels an "
+                        "observation touches, so DRAM traffic is below the algorithmic bytes and the kernel is "
+                        "instruction-issue bound (see profiles/)"}
+
+    # per-frame (K = 1) kernel on a frame subset: the north-star's ">= 70 % of HBM roofline" line
+    k1_frames = min(F, 32)
+    vol1 = pkg.Volume(grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin, synth.CAM_K, z_range=(z0, z1),
+                      device=local_rank, max_batch=1, cull_level=args.cull, tuning=args.tuning)
+    vol1.integrate_batch(depth, poses, n_frames=min(4, F))
+    vol1.reset()
+    vol1.synchronize()
+    vol1.timer_start()
+    vol1.integrate_batch(depth, poses, n_frames=k1_frames)
+    ms_k1 = max_over_ranks(vol1.timer_stop())
+    vol1.close()
+    ach1 = alg_bytes_per_launch / (ms_k1 / k1_frames * 1e-3) / 1e9
+    roofline_k1 = {"bound": "hbm", "achieved": round(ach1, 1), "peak": peak, "unit": "GB/s",
+                   "frac": round(ach1 / peak, 4), "frames": k1_frames, "avg_launch_ms": round(ms_k1 / k1_frames, 4),
+                   "updates_per_sec": total_voxels * k1_frames / (ms_k1 * 1e-3)}
+
+    # ---- e2e: host buffers through the C ABI, H2D + fusion + extraction + D2H of the points ---------
+    depth_host = torch.empty(depth.shape, dtype=torch.float32, pin_memory=True)
+    depth_host.copy_(depth)
+    torch.cuda.synchronize()
+    pts_host = None
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def step_e2e():
+        nonlocal pts_host
+        vol.reset()
+        vol.integrate_batch(depth_host, poses)
+        n = vol.extract_surface_count()
+        if pts_host is None or pts_host.shape[0] < n:
+            pts_host = np.empty((int(n * 1.2) + 16, 3), np.float32)
+        pkg.binding._check(vol._lib.tsdf_copy_surface(vol._h, pts_host.ctypes.data, pts_host.shape[0]), "copy_surface")
+        return n
+
+    step_e2e()
+    barrier()
+    vol.reset_stats()
+    t0 = time.perf_counter()
+    n_pts = 0
+    for _ in range(e2e_steps):
+        n_pts = step_e2e()
+    vol.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    st = vol.stats()
+    e2e_value = total_voxels * F / (t_e2e / e2e_steps)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st["h2d_bytes"] / e2e_steps + poses.nbytes),
+           "d2h_bytes_per_step": int(st["d2h_bytes"] / e2e_steps), "steps": e2e_steps,
+           "ms_per_step": round(t_e2e / e2e_steps * 1e3, 2), "surface_points_rank0": int(n_pts),
+           "path": "tsdf_reset + tsdf_integrate_batch(pinned host depth) + tsdf_extract_surface + tsdf_copy_surface"}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(pkg, cfg, depth[:64].cpu().numpy(), poses[:64], target_s=args.cpu_seconds)
+
+    vol.close()
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{grid.dims[0]}^3 grid ({grid.voxel_size * 1e3:.1f} mm voxels), {F} frames 640x480, "
+                                   f"K={args.batch} frames per pass, z-slab sharded over {world} GPU(s)",
+                       "config_key": args.config, "frames": F, "batch": args.batch, "cull_level": args.cull,
+                       "l2": "volume (>= 1 GB per GPU) is larger than L2; no flush needed",
+                       "parallelism": f"z-slab x{world}"},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_k1": roofline_k1,
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(pkg, cfg, depth, poses, target_s=12.0, force_port=False):
+    """Reference Integrate body on host threads (oracle/_ref) or the oracle port, bounded sample."""
+    oracle = graft.load_oracle()
+    grid = cfg["grid"]
+    dx, dy, dz = grid.dims
+    nz = max(1, min(dz, (64 * 1024 * 1024) // (dx * dy)))  # <= 64 Mi voxels (512 MB) of the grid's far half
+    z0 = min(dz - nz, dz // 2)
+    K = pkg.synth.CAM_K
+    use_ref = oracle.have_ref_host() and not force_port
+
+    def run(n_frames):
+        t0 = time.perf_counter()
+        if use_ref:
+            # the reference kernel addresses the grid from z = 0: shift the origin by z0 planes
+            oz = float(np.float32(grid.origin[2]) + np.float32(z0) * np.float32(grid.voxel_size))
+            oracle.ref_host_fuse(K, poses[:n_frames], depth[:n_frames], (dx, dy, nz),
+                                 (grid.origin[0], grid.origin[1], oz), grid.voxel_size, grid.trunc_margin)
+        else:
+            oracle.fuse(K, poses[:n_frames], depth[:n_frames], grid.dims, grid.origin, grid.voxel_size,
+                        grid.trunc_margin, z_range=(z0, z0 + nz))
+        return time.perf_counter() - t0
+
+    t1 = run(1)
+    n = int(max(1, min(len(poses), target_s / max(t1, 1e-3))))
+    t = run(n)
+    cores = oracle.ref_host_num_threads() if use_ref else oracle.num_threads()
+    return {"value": dx * dy * nz * n / t, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": f"z-planes [{z0}, {z0 + nz}) of the {dx}x{dy}x{dz} grid x {n} frames "
+                      f"({dx * dy * nz * n / 1e9:.2f} G voxel-updates in {t:.1f} s), "
+                      + ("reference Integrate body (demo.cu:18-68) compiled for the host, OpenMP over (z, y)"
+                         if use_ref else "oracle port (oracle/tsdf_oracle.c), OpenMP over rows")}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU-executable implementation of the path (its Integrate body
+    compiled for the host, oracle/_ref/libref_host.so; else the oracle port) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    pkg = graft.load_package()
+    oracle = graft.load_oracle()
+    synth = pkg.synth
+    cfg = dict(synth.CONFIGS[args.config])
+    if args.frames:
+        cfg["frames"] = args.frames
+    grid, F = cfg["grid"], cfg["frames"]
+    n_frames = 2
+    frames = list(range(n_frames))
+    mm = synth.mm_to_u16_numpy(synth.render_depth_mm(frames, device="cpu"))
+    depth = oracle.depth_from_u16(mm)
+    c2w, b2w = synth.make_poses(frames)
+    poses = np.stack([oracle.cam2base_from_world(b2w, m).ravel() for m in c2w]).astype(np.float32)
+    dx, dy, dz = grid.dims
+    nz = max(1, min(dz, (32 * 1024 * 1024) // (dx * dy)))
+    z0 = min(dz - nz, dz // 2)
+    use_ref = oracle.have_ref_host()
+    oz = float(np.float32(grid.origin[2]) + np.float32(z0) * np.float32(grid.voxel_size))
+
+    def step():
+        if use_ref:
+            oracle.ref_host_fuse(synth.CAM_K, poses, depth, (dx, dy, nz), (grid.origin[0], grid.origin[1], oz),
+                                 grid.voxel_size, grid.trunc_margin)
+        else:
+            oracle.fuse(synth.CAM_K, poses, depth, grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin,
+                        z_range=(z0, z0 + nz))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    t = time.perf_counter() - t0
+    updates = dx * dy * nz * n_frames
+    value = updates * args.steps / t
+    cores = oracle.ref_host_num_threads() if use_ref else oracle.num_threads()
+    sample = (f"each step: z-planes [{z0}, {z0 + nz}) of the {dx}x{dy}x{dz} grid x {n_frames} frames "
+              f"= {updates / 1e6:.0f} M voxel-updates")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 2), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{grid.dims[0]}^3 grid ({grid.voxel_size * 1e3:.1f} mm voxels), {F} frames 640x480 "
+                               f"(bounded sample per step, see cpu_baseline.sample)", "config_key": args.config},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", default="1024", choices=["1024", "512", "demo500"])
+    ap.add_argument("--frames", type=int, default=0, help="override the configuration's frame count")
+    ap.add_argument("--batch", type=int, default=16, help="K: frames fused per pass over the volume")
+    ap.add_argument("--cull", type=int, default=2)
+    ap.add_argument("--tuning", type=int, default=0, help="kernel tuning variant (bits 0-7) | 256 = exact path only")
+    ap.add_argument("--quick", action="store_true", help="value only: skip e2e, K=1 roofline and CPU baseline")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

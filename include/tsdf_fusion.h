@@ -59,7 +59,7 @@ typedef struct tsdf_volume_desc {
   int32_t device;                       /* CUDA device ordinal */
   int32_t max_batch;                    /* K: 1..TSDF_MAX_BATCH, 0 = default */
   int32_t cull_level;                   /* 0 none, 1 per-thread frustum cull, 2 + per-tile frame mask (default: -1 = 2) */
-  int32_t reserved0;
+  int32_t reserved0;                    /* 0; (internal tuning / validation switches) */
   void *stream;                         /* cudaStream_t to run on; NULL = the engine creates its own */
   float *ext_tsdf, *ext_weight;         /* optional caller-owned DEVICE slabs to adopt (NULL = engine-owned) */
 } tsdf_volume_desc;

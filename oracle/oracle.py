@@ -17,6 +17,7 @@ HERE = Path(__file__).resolve().parent
 ORACLE_LIB = HERE / "_build" / "liboracle.so"
 REF_HOST_LIB = HERE / "_ref" / "libref_host.so"
 REF_CUDA_LIB = HERE / "_ref" / "libref_cuda.so"
+REF_CUDA_NOFMAD_LIB = HERE / "_ref" / "libref_cuda_nofmad.so"
 
 _cache = {}
 
@@ -200,8 +201,9 @@ def ref_host_num_threads():
 
 # ---- the reference kernel on the GPU (oracle/_ref/libref_cuda.so) -----------------------------------
 
-def ref_cuda_fuse(cam_K, cam2base, depth_frames, dims, origin, voxel_size, trunc_margin, download=True):
-    """Returns (tsdf, weight, kernel_ms) from the reference's Integrate<<<dim_z, dim_y>>> on the GPU."""
+def ref_cuda_fuse(cam_K, cam2base, depth_frames, dims, origin, voxel_size, trunc_margin, download=True, fmad=True):
+    """Returns (tsdf, weight, kernel_ms) from the reference's Integrate<<<dim_z, dim_y>>> on the GPU
+    (fmad=True: built like depth-fusion/compile.sh:18; fmad=False: the same file with --fmad=false)."""
     dx, dy, dz = (int(v) for v in dims)
     poses = _f32(cam2base).reshape(-1, 16)
     depth = _f32(depth_frames)
@@ -211,7 +213,7 @@ def ref_cuda_fuse(cam_K, cam2base, depth_frames, dims, origin, voxel_size, trunc
     t = np.empty(dx * dy * dz, np.float32) if download else None
     w = np.empty(dx * dy * dz, np.float32) if download else None
     ms = C.c_float(0)
-    rc = _load(REF_CUDA_LIB).ref_cuda_fuse(
+    rc = _load(REF_CUDA_LIB if fmad else REF_CUDA_NOFMAD_LIB).ref_cuda_fuse(
         _p(K), _p(poses), _p(depth), C.c_int(n), C.c_int(im_h), C.c_int(im_w), C.c_int(dx), C.c_int(dy), C.c_int(dz),
         C.c_float(origin[0]), C.c_float(origin[1]), C.c_float(origin[2]), C.c_float(voxel_size),
         C.c_float(trunc_margin), _p(t) if download else None, _p(w) if download else None, C.byref(ms))
