@@ -3,7 +3,7 @@
 
 The directory name is not a Python identifier; load it with `__graft_entry__.load_package()`.
 """
-from . import binding, synth  # noqa: F401
+from . import binding, sharding, synth  # noqa: F401
 from .binding import (  # noqa: F401
     Integrate, LoadMatrixFromFile, ReadDepth, SaveVoxelGrid2SurfacePointCloud, TsdfError, Volume,
     cam2base_from_world, depth_from_u16, invert_matrix, load_library, multiply_matrix, write_bin, write_ply,

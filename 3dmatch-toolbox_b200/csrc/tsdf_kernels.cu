@@ -557,10 +557,10 @@ cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
   if (p.dim_x % 4 != 0) return launch_integrate_t<1, 4, false, 3>(p, nullptr, nullptr, s);
   switch (p.variant) {  // tuning variants (tsdf_volume_desc.reserved0); 0 is the production choice
     case 1: return launch_integrate_t<4, 4, false, 2>(p, nullptr, nullptr, s);
-    case 2: return launch_integrate_t<4, 4, false, 4>(p, nullptr, nullptr, s);
+    case 2: return launch_integrate_t<4, 4, false, 3>(p, nullptr, nullptr, s);
     case 3: return launch_integrate_t<4, 2, false, 4>(p, nullptr, nullptr, s);
     case 4: return launch_integrate_t<4, 2, false, 5>(p, nullptr, nullptr, s);
-    default: return launch_integrate_t<4, 4, false, 3>(p, nullptr, nullptr, s);
+    default: return launch_integrate_t<4, 4, false, 4>(p, nullptr, nullptr, s);
   }
 }
 

@@ -110,8 +110,7 @@ def build_inputs(pkg, cfg, device, rank, world, dist):
     if rank == 0:
         for f0 in range(0, F, 50):
             mm[f0:f0 + 50] = synth.render_depth_mm(frames[f0:f0 + 50], device=device)
-    if world > 1:
-        dist.broadcast(mm, src=0)
+    pkg.sharding.broadcast_frames(mm, src=0)  # NCCL over NVLink when world > 1
     # utils.hpp:82-84 on the device: (float)mm / 1000.0f (IEEE division), > 6 -> 0
     depth = torch.div(mm.to(torch.float32), torch.full((1,), 1000.0, dtype=torch.float32, device=device))
     depth = torch.where(depth > 6.0, torch.zeros_like(depth), depth).contiguous()
@@ -123,10 +122,6 @@ def build_inputs(pkg, cfg, device, rank, world, dist):
     del mm
     torch.cuda.synchronize()  # the engine runs on its own stream
     return depth, poses
-
-
-def slab_range(dim_z, rank, world):
-    return (dim_z * rank) // world, (dim_z * (rank + 1)) // world
 
 
 def run_ours(args):
@@ -169,7 +164,7 @@ def run_ours(args):
     if args.frames:
         cfg["frames"] = args.frames
     grid, F = cfg["grid"], cfg["frames"]
-    z0, z1 = slab_range(grid.dims[2], rank, world)
+    z0, z1 = pkg.sharding.slab_range(grid.dims[2], rank, world)
     depth, poses = build_inputs(pkg, cfg, device, rank, world, dist)
 
     vol = pkg.Volume(grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin, synth.CAM_K, z_range=(z0, z1),

@@ -1,0 +1,121 @@
+"""The drop-in CLI (3dmatch-toolbox_b200/bin/demo) on a synthetic sequence written to disk in the
+reference's input formats (camera-intrinsics.txt, frame-%06d.pose.txt, frame-%06d.depth.png):
+argv[1..10] as depth-fusion/fuseSceneFragments.m:63-64 passes them, tsdf.ply / tsdf.bin compared
+byte for byte with the oracle pipeline, stdout lines as demo.cu:177,191."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+DEMO = ROOT / "3dmatch-toolbox_b200" / "bin" / "demo"
+
+
+def write_matrix(path, m):
+    # the sample's pose files: tab separated, %15.7e style with 3-digit exponents is also accepted
+    path.write_text("".join("\t".join(f" {v: .8e}" for v in row) + "\t\n" for row in np.asarray(m)))
+
+
+def write_sequence(tmp_path, synth, frames, first_idx):
+    import cv2
+    data = tmp_path / "seq-01"
+    data.mkdir()
+    mm = synth.mm_to_u16_numpy(synth.render_depth_mm(frames))
+    c2w, _ = synth.make_poses(frames)
+    for i, f in enumerate(frames):
+        assert cv2.imwrite(str(data / f"frame-{first_idx + i:06d}.depth.png"), mm[i])
+        write_matrix(data / f"frame-{first_idx + i:06d}.pose.txt", c2w[i])
+    write_matrix(tmp_path / "camera-intrinsics.txt", synth.CAM_K.reshape(3, 3))
+    return data, mm, c2w
+
+
+def oracle_pipeline(oracle, synth, data, mm, first_idx, n, dims, origin, voxel, trunc):
+    K = oracle.load_matrix(data.parent / "camera-intrinsics.txt", 9)[1]
+    base = oracle.load_matrix(data / f"frame-{first_idx:06d}.pose.txt", 16)[1]
+    poses = np.stack([oracle.cam2base_from_world(base, oracle.load_matrix(data / f"frame-{first_idx + i:06d}.pose.txt", 16)[1]).ravel()
+                      for i in range(n)])
+    depth = oracle.depth_from_u16(mm[:n])
+    t, w = oracle.fuse(K, poses, depth, dims, origin, voxel, trunc)
+    return t, w, oracle.extract_surface(t, w, dims, origin, voxel)
+
+
+def test_cli_reference_argv_and_outputs(pkg, oracle, synth, tmp_path):
+    frames = [0, 6, 12, 18, 24, 30, 36]
+    data, mm, _ = write_sequence(tmp_path, synth, frames, first_idx=100)
+    dims = (96, 96, 96)
+    # exactly the MATLAB caller's format string: %s %s %d %d %f %f %f %f %f %f
+    argv = [str(DEMO), str(tmp_path / "camera-intrinsics.txt"), str(data), "100", "100", "%f" % 7, "%f" % -1.5,
+            "%f" % -1.5, "%f" % 0.5, "%f" % 0.03125, "%f" % 0.15625, "--dim", "96", "--bin", "--batch", "3"]
+    run = subprocess.run(argv, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    lines = run.stdout.splitlines()
+    assert lines[:7] == [f"Fusing: {data}/frame-{100 + i:06d}.depth.png" for i in range(7)]  # demo.cu:177
+    assert lines[7] == "Saving surface point cloud (tsdf.ply)..."                             # demo.cu:191
+    voxel, trunc = float(np.float32(0.03125)), float(np.float32(0.15625))
+    t, w, pts = oracle_pipeline(oracle, synth, data, mm, 100, 7, dims, (-1.5, -1.5, 0.5), voxel, trunc)
+    assert len(pts) > 100
+    oracle.write_ply(tmp_path / "oracle.ply", pts)
+    assert (tmp_path / "tsdf.ply").read_bytes() == (tmp_path / "oracle.ply").read_bytes()
+    oracle.write_tsdf_bin(tmp_path / "oracle.bin", dims, (-1.5, -1.5, 0.5), voxel, trunc, t)
+    assert (tmp_path / "tsdf.bin").read_bytes() == (tmp_path / "oracle.bin").read_bytes()
+
+
+def test_cli_base_frame_differs_from_first_frame(pkg, oracle, synth, tmp_path):
+    """argv[3] (base_frame_idx) and argv[4] (first_frame_idx) are independent (demo.cu:105-106)."""
+    frames = [0, 5, 10, 15]
+    data, mm, c2w = write_sequence(tmp_path, synth, frames, first_idx=0)
+    argv = [str(DEMO), str(tmp_path / "camera-intrinsics.txt"), str(data), "0", "1", "3", "-1.5", "-1.5", "0.5",
+            "0.047", "0.235", "--dim", "64", "--ply", "out.ply"]
+    run = subprocess.run(argv, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    K = synth.CAM_K
+    poses = np.stack([oracle.cam2base_from_world(c2w[0], c2w[i]).ravel() for i in (1, 2, 3)])
+    depth = oracle.depth_from_u16(mm[1:4])
+    voxel, trunc = float(np.float32(0.047)), float(np.float32(0.235))
+    t, w = oracle.fuse(K, poses, depth, (64, 64, 64), (-1.5, -1.5, 0.5), voxel, trunc)
+    oracle.write_ply(tmp_path / "oracle.ply", oracle.extract_surface(t, w, (64, 64, 64), (-1.5, -1.5, 0.5), voxel))
+    assert (tmp_path / "out.ply").read_bytes() == (tmp_path / "oracle.ply").read_bytes()
+
+
+def test_cli_error_behaviour(tmp_path, synth):
+    """Missing inputs: message + `FatalError. Program Terminated.` on stderr, EXIT_FAILURE (utils.hpp:240-253)."""
+    run = subprocess.run([str(DEMO), "nope.txt", str(tmp_path), "0", "0", "1", "-1.5", "-1.5", "0.5", "0.006", "0.03"],
+                         cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert run.returncode == 1 and "FatalError. Program Terminated." in run.stderr
+    write_matrix(tmp_path / "K.txt", synth.CAM_K.reshape(3, 3))
+    write_matrix(tmp_path / "frame-000000.pose.txt", np.eye(4))
+    run = subprocess.run([str(DEMO), "K.txt", ".", "0", "0", "1", "-1.5", "-1.5", "0.5", "0.05", "0.25", "--dim", "32"],
+                         cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert run.returncode == 1
+    assert "Error: depth image file not read!" in run.stdout  # utils.hpp:77
+    run = subprocess.run([str(DEMO), "K.txt", "."], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert run.returncode == 1 and "usage" in run.stderr
+
+
+def test_cli_real_sample_frame(pkg, oracle, tmp_path):
+    """One frame of the reference's sample sequence (committed fixture) through PNG decode + fusion."""
+    png, pose = GOLDEN / "frame-000008.depth.png", GOLDEN / "frame-000008.pose.txt"
+    if not png.exists():
+        pytest.skip("fixture not generated")
+    import cv2
+    (tmp_path / "frame-000008.depth.png").write_bytes(png.read_bytes())
+    (tmp_path / "frame-000008.pose.txt").write_bytes(pose.read_bytes())
+    (tmp_path / "K.txt").write_text("585 0 320\n0 585 240\n0 0 1\n")
+    run = subprocess.run([str(DEMO), "K.txt", ".", "8", "8", "1", "-1.5", "-1.5", "0.5", "0.012", "0.06", "--dim", "250",
+                          "--thresh", "0.2", "0.0", "--bin"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    mm = cv2.imread(str(png), cv2.IMREAD_UNCHANGED)
+    base = oracle.load_matrix(pose, 16)[1]
+    K = np.float32([585, 0, 320, 0, 585, 240, 0, 0, 1])
+    voxel, trunc = float(np.float32(0.012)), float(np.float32(0.06))
+    t, w = oracle.fuse(K, oracle.cam2base_from_world(base, base).reshape(1, 16), oracle.depth_from_u16(mm)[None],
+                       (250, 250, 250), (-1.5, -1.5, 0.5), voxel, trunc)
+    pts = oracle.extract_surface(t, w, (250, 250, 250), (-1.5, -1.5, 0.5), voxel, 0.2, 0.0)
+    assert len(pts) > 1000
+    oracle.write_ply(tmp_path / "oracle.ply", pts)
+    assert (tmp_path / "tsdf.ply").read_bytes() == (tmp_path / "oracle.ply").read_bytes()
+    raw = np.fromfile(tmp_path / "tsdf.bin", np.float32)
+    assert np.array_equal(raw[8:].view(np.uint32), t.ravel().view(np.uint32))
