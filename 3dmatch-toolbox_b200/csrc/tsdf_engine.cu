@@ -113,6 +113,7 @@ void fill_params(const tsdf_volume* v, tsdf::IntegrateParams* p) {
   p->cull_level = v->cull;
   p->fast_level = (v->tuning & 0x100) ? 0 : 1;
   p->variant = v->tuning & 0xff;
+  p->force_lx = (v->tuning >> 12) & 0xff;
 }
 
 void pose_from_cam2base(const float* c, tsdf::FramePose* o) {
@@ -127,6 +128,7 @@ int launch_chunk(tsdf_volume* v, const float* dev_depth, const float* cam2base, 
   tsdf::IntegrateParams p;
   fill_params(v, &p);
   p.depth = dev_depth;
+  p.sanitized = 1;  // every depth frame reaches the kernel through sanitize / depth_from_u16(sanitize)
   p.n_frames = n;
   for (int f = 0; f < n; ++f) pose_from_cam2base(cam2base + 16 * f, &p.pose[f]);
   make_cull_margins(v, p.pose, n, &p);
@@ -200,10 +202,11 @@ int integrate_from_host(tsdf_volume* v, int n_frames, const Src* src, const floa
     v->stats.h2d_bytes += (int64_t)(elems * sizeof(Src));
     CK(cudaEventRecord(v->ev_copied[s], v->copy_stream));
     CK(cudaStreamWaitEvent(v->stream, v->ev_copied[s], 0));
-    if (u16) {
-      CK(tsdf::launch_depth_from_u16(v->dev_mm[s], v->dev_depth[s], (int64_t)elems, v->stream));
-      v->stats.kernel_launches += 1;
-    }
+    if (u16)
+      CK(tsdf::launch_depth_from_u16(v->dev_mm[s], v->dev_depth[s], (int64_t)elems, true, v->stream));
+    else
+      CK(tsdf::launch_sanitize_depth(v->dev_depth[s], v->dev_depth[s], (int64_t)elems, v->stream));
+    v->stats.kernel_launches += 1;
     rc = launch_chunk(v, v->dev_depth[s], cam2base + 16 * (size_t)f0, n);
     if (rc) return rc;
     CK(cudaEventRecord(v->ev_consumed[s], v->stream));
@@ -367,9 +370,15 @@ int tsdf_integrate_batch(tsdf_volume* v, int32_t n_frames, const float* depth_fr
   if (int rc = use_device(v)) return rc;
   const MemKind kind = classify(depth_frames);
   if (kind == MemKind::Device) {
+    if (int rc = ensure_ring(v, false)) return rc;
     for (int f0 = 0; f0 < n_frames; f0 += v->batch) {
       const int n = (n_frames - f0 < v->batch) ? n_frames - f0 : v->batch;
-      if (int rc = launch_chunk(v, depth_frames + (size_t)f0 * v->frame_px, cam2base + 16 * (size_t)f0, n)) return rc;
+      const int s = (int)(v->ring_pos++ % kSlots);
+      // the caller's frames stay untouched: invalid pixels are marked in the engine's own copy
+      CK(tsdf::launch_sanitize_depth(depth_frames + (size_t)f0 * v->frame_px, v->dev_depth[s], (int64_t)n * v->frame_px,
+                                     v->stream));
+      v->stats.kernel_launches += 1;
+      if (int rc = launch_chunk(v, v->dev_depth[s], cam2base + 16 * (size_t)f0, n)) return rc;
     }
     return TSDF_OK;
   }
@@ -387,7 +396,7 @@ int tsdf_integrate_batch_u16(tsdf_volume* v, int32_t n_frames, const uint16_t* d
       const int n = (n_frames - f0 < v->batch) ? n_frames - f0 : v->batch;
       const int s = (int)(v->ring_pos++ % kSlots);
       CK(tsdf::launch_depth_from_u16(depth_mm + (size_t)f0 * v->frame_px, v->dev_depth[s], (int64_t)n * v->frame_px,
-                                     v->stream));
+                                     true, v->stream));
       v->stats.kernel_launches += 1;
       if (int rc = launch_chunk(v, v->dev_depth[s], cam2base + 16 * (size_t)f0, n)) return rc;
     }

@@ -36,6 +36,8 @@ struct IntegrateParams {
   float cull_gx, cull_gy, cull_z;  // conservative margins (see make_cull_margins)
   int fast_level;        // 0: every voxel through the exact path, 1: fast classification first
   int variant;           // tuning variant of the kernel instantiation (0 = production)
+  int force_lx;          // tuning: threads of a warp laid along x (0 = choose by lane waste)
+  int sanitized;         // depth frames went through sanitize_depth_kernel (invalid = -inf)
   float lim_x, lim_y;    // filled by the launcher: 0.5 - pixel_round_margin()
   FramePose pose[kMaxBatch];
 };
@@ -67,7 +69,8 @@ cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s);
 // Pose and intrinsics read from DEVICE memory (reference-style Integrate argument list).
 cudaError_t launch_integrate_devpose(IntegrateParams p, const float* d_cam_K, const float* d_cam2base,
                                      cudaStream_t s);
-cudaError_t launch_depth_from_u16(const uint16_t* mm, float* depth, int64_t n, cudaStream_t s);
+cudaError_t launch_depth_from_u16(const uint16_t* mm, float* depth, int64_t n, bool sanitize, cudaStream_t s);
+cudaError_t launch_sanitize_depth(const float* in, float* out, int64_t n, cudaStream_t s);
 cudaError_t launch_extract_count(const ExtractParams& p, unsigned long long* tile_counts, int64_t n_tiles,
                                  cudaStream_t s);
 cudaError_t launch_extract_scan(unsigned long long* tile_counts, int64_t n_tiles, unsigned long long* total,
