@@ -789,8 +789,8 @@ cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
     case 8: return launch_integrate_t<4, 8, false, 4, true, true>(p, nullptr, nullptr, s);
     case 9: return launch_integrate_t<4, 8, false, 3, true, true>(p, nullptr, nullptr, s);
     case 10: return launch_integrate_t<4, 4, false, 6, true, true>(p, nullptr, nullptr, s);
-    case 11: return launch_integrate_t<4, 8, false, 5, true, true>(p, nullptr, nullptr, s);
-    default: return launch_integrate_t<4, 8, false, 4, true, true>(p, nullptr, nullptr, s);
+    case 11: return launch_integrate_t<4, 8, false, 4, true, true>(p, nullptr, nullptr, s);
+    default: return launch_integrate_t<4, 8, false, 5, true, true>(p, nullptr, nullptr, s);
   }
 }
 

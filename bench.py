@@ -225,7 +225,7 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "kernel": "integrate_kernel<4,4>", "frames_per_launch": args.batch,
+                "kernel": "integrate_pending_kernel<VEC=4,ZT=8>", "frames_per_launch": args.batch,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": round(ms_int / n_launch, 4),
                 "updates_per_sec_roofline": peak * 1e9 / BYTES_PER_VOXEL_PASS * args.batch,
@@ -354,7 +354,7 @@ def run_reference(args):
     if args.frames:
         cfg["frames"] = args.frames
     grid, F = cfg["grid"], cfg["frames"]
-    n_frames = 2
+    n_frames = 8
     frames = list(range(n_frames))
     mm = synth.mm_to_u16_numpy(synth.render_depth_mm(frames, device="cpu"))
     depth = oracle.depth_from_u16(mm)

@@ -277,3 +277,94 @@ def test_engine_vs_golden_vectors(pkg, name):
         if "ply" in g:
             payload = g["ply"].tobytes().split(b"end_header\n", 1)[1]
             assert pts.tobytes() == payload
+
+
+def test_full_size_1024_sampled_planes_and_properties(pkg, oracle, sequence):
+    """BASELINE config 3 geometry (1024^3, 3 mm voxels, 1.5 cm truncation) at full size: the oracle is
+    evaluated on sampled z-planes (voxels are independent), and K-batched == per-frame
+    through a checksum of the whole volume."""
+    import torch
+    frames = [0, 3, 7, 12, 40, 41, 500, 999]
+    depth, _, poses, K = sequence(frames)
+    dims, voxel, trunc = (1024, 1024, 1024), 0.003, 0.015
+    n = dims[0] * dims[1] * dims[2]
+    sums = []
+    for batch in (8, 1):
+        t_dev = torch.empty(n, dtype=torch.float32, device="cuda")
+        w_dev = torch.empty(n, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        with pkg.Volume(dims, ORIGIN, voxel, trunc, K, max_batch=batch, ext_tsdf=t_dev, ext_weight=w_dev) as vol:
+            vol.reset()
+            vol.integrate_batch(depth, poses)
+            vol.synchronize()
+            n_pts = vol.extract_surface_count()
+        tv, wv = t_dev.view(1024, 1024, 1024), w_dev.view(1024, 1024, 1024)
+        sums.append((int(t_dev.view(torch.int32).to(torch.int64).sum().item()), float(w_dev.double().sum().item()), n_pts))
+        if batch == 8:
+            planes = [0, 1, 255, 256, 511, 512, 767, 1023]
+            for z in planes:
+                t_ref, w_ref = oracle.fuse(K, poses, depth, dims, ORIGIN, voxel, trunc, z_range=(z, z + 1))
+                assert_bit_equal(wv[z].cpu().numpy(), w_ref[0], f"weights plane {z}")
+                assert_bit_equal(tv[z].cpu().numpy(), t_ref[0], f"tsdf plane {z}")
+            assert float(w_dev.max().item()) == len(frames)
+        del t_dev, w_dev, tv, wv
+    assert sums[0] == sums[1], f"K=8 vs K=1 checksums differ: {sums}"
+    assert sums[0][2] > 10000
+
+
+def test_2048_cube_64bit_indexing_sampled_planes(pkg, oracle, sequence):
+    """BASELINE config 4 geometry (2048^3 = 2^33 voxels, 69 GB: beyond int32 indices and the reference's
+    1024-thread block limit) on ONE GPU, checked on sampled planes incl. the ones past the 2^32 voxel mark."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100 * 2**30:
+        pytest.skip("needs > 100 GB of HBM")
+    frames = [0, 25, 700]
+    depth, _, poses, K = sequence(frames)
+    dims, voxel, trunc = (2048, 2048, 2048), 0.0015, 0.0075
+    n = dims[0] * dims[1] * dims[2]
+    t_dev = torch.empty(n, dtype=torch.float32, device="cuda")
+    w_dev = torch.empty(n, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with pkg.Volume(dims, ORIGIN, voxel, trunc, K, max_batch=3, ext_tsdf=t_dev, ext_weight=w_dev) as vol:
+        vol.reset()
+        vol.integrate_batch(depth, poses)
+        vol.synchronize()
+        pts = vol.extract_surface(0.2, 0.0)
+    tv, wv = t_dev.view(2048, 2048, 2048), w_dev.view(2048, 2048, 2048)
+    total = 0
+    for z in (0, 1023, 1024, 1500, 2047):
+        t_ref, w_ref = oracle.fuse(K, poses, depth, dims, ORIGIN, voxel, trunc, z_range=(z, z + 1))
+        assert_bit_equal(wv[z].cpu().numpy(), w_ref[0], f"weights plane {z}")
+        assert_bit_equal(tv[z].cpu().numpy(), t_ref[0], f"tsdf plane {z}")
+        ref_pts = oracle.extract_surface(t_ref, w_ref, dims, ORIGIN, voxel, 0.2, 0.0, z_range=(z, z + 1))
+        zc = np.float32(ORIGIN[2]) + np.float32(z) * np.float32(voxel)
+        got = pts[pts[:, 2] == zc]
+        assert_bit_equal(got, ref_pts, f"surface points of plane {z}")
+        total += len(ref_pts)
+    assert total > 1000
+    # ascending linear index: z never decreases along the point list (utils.hpp:36-53)
+    assert np.all(np.diff(pts[:, 2]) >= 0)
+
+
+def test_fragment_batch_independent_volumes(pkg, oracle, sequence, synth):
+    """BASELINE config 5 in miniature (fuseSceneFragments.m:36-81): independent fragment volumes, each
+    with its own base frame, fused concurrently on separate streams of one GPU."""
+    frag_frames = 6
+    n_frag = 5
+    dims, voxel, trunc = (120, 120, 120), 0.025, 0.125
+    vols, refs = [], []
+    for i in range(n_frag):
+        frames = list(range(50 * i, 50 * i + frag_frames * 8, 8))
+        depth, _, poses, K = sequence(frames, base_frame=50 * i)
+        vols.append((pkg.Volume(dims, ORIGIN, voxel, trunc, K, max_batch=4), depth, poses))
+        refs.append((K, poses, depth))
+    for vol, depth, poses in vols:          # enqueue everything first: handles own independent streams
+        vol.integrate_batch(depth, poses)
+    for (vol, _, _), (K, poses, depth) in zip(vols, refs):
+        t, w = vol.download()
+        pts = vol.extract_surface()
+        t_ref, w_ref = oracle.fuse(K, poses, depth, dims, ORIGIN, voxel, trunc)
+        assert_bit_equal(w, w_ref, "fragment weights")
+        assert_bit_equal(t, t_ref, "fragment tsdf")
+        assert_bit_equal(pts, oracle.extract_surface(t_ref, w_ref, dims, ORIGIN, voxel), "fragment points")
+        vol.close()
