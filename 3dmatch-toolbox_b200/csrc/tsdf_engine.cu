@@ -32,7 +32,8 @@ int set_err(int code, const char* fmt, ...) {
       return set_err(TSDF_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
   } while (0)
 
-constexpr int kSlots = 3;  // staging ring depth for host-resident input
+constexpr int kSlots = 3;   // staging ring depth (K-frame depth slots)
+constexpr int kMaxSub = 4;  // concurrent sub-slab streams per handle
 
 }  // namespace
 
@@ -52,8 +53,15 @@ struct tsdf_volume {
   float* pin_depth[kSlots] = {};
   uint16_t* dev_mm[kSlots] = {};
   uint16_t* pin_mm[kSlots] = {};
-  cudaEvent_t ev_copied[kSlots] = {}, ev_consumed[kSlots] = {};
+  cudaEvent_t ev_copied[kSlots] = {}, ev_ready[kSlots] = {};
+  cudaEvent_t ev_join[kSlots][kMaxSub] = {};  // sub-stream i finished reading slot s
   bool slot_busy[kSlots] = {};
+  // the slab is fused as n_sub z sub-slabs on their own streams: consecutive K-frame passes of one
+  // sub-slab are ordered, different sub-slabs overlap, which hides the tail of every launch
+  int n_sub = 1;
+  cudaStream_t sub_stream[kMaxSub] = {};
+  int64_t sub_z[kMaxSub + 1] = {};  // sub-slab i = local planes [sub_z[i], sub_z[i+1])
+  int last_slot = -1;
   int64_t ring_pos = 0;
   // surface extraction
   unsigned long long* tile_offsets = nullptr;
@@ -123,19 +131,60 @@ void pose_from_cam2base(const float* c, tsdf::FramePose* o) {
   o->tx = c[3]; o->ty = c[7]; o->tz = c[11];
 }
 
-// Launch one pass over the slab for `n` (<= batch) frames whose depth is on the device.
-int launch_chunk(tsdf_volume* v, const float* dev_depth, const float* cam2base, int n) {
+// Launch one pass over the slab for `n` (<= batch) frames whose (sanitized) depth sits in ring slot
+// `slot`.  The producer of the slot ran on v->stream; the sub-slab kernels fork from there onto the
+// sub-streams and are joined back only by join_substreams() at the end of an API call.
+int launch_chunk(tsdf_volume* v, int slot, const float* cam2base, int n) {
   tsdf::IntegrateParams p;
   fill_params(v, &p);
-  p.depth = dev_depth;
+  p.depth = v->dev_depth[slot];
   p.sanitized = 1;  // every depth frame reaches the kernel through sanitize / depth_from_u16(sanitize)
   p.n_frames = n;
   for (int f = 0; f < n; ++f) pose_from_cam2base(cam2base + 16 * f, &p.pose[f]);
   make_cull_margins(v, p.pose, n, &p);
-  CK(tsdf::launch_integrate(p, v->stream));
-  v->stats.kernel_launches += 1;
+  {
+    // planes further from the cameras (along z) intersect more of the frusta and cost more: start there
+    float tz = 0.f;
+    for (int f = 0; f < n; ++f) tz += p.pose[f].tz;
+    const float mid = v->d.origin_z + 0.5f * (float)(v->d.z_begin + v->d.z_end) * v->d.voxel_size;
+    p.z_reverse = ((tz / (float)n) < mid) ? 1 : 0;
+    if (v->tuning & 0x200) p.z_reverse = !p.z_reverse;
+  }
+  const int64_t plane = v->d.dim_x * v->d.dim_y;
+  CK(cudaEventRecord(v->ev_ready[slot], v->stream));
+  for (int i = 0; i < v->n_sub; ++i) {
+    tsdf::IntegrateParams q = p;
+    q.tsdf = v->tsdf + v->sub_z[i] * plane;
+    q.weight = v->weight + v->sub_z[i] * plane;
+    q.nz = (int)(v->sub_z[i + 1] - v->sub_z[i]);
+    q.z_begin = (int)(v->d.z_begin + v->sub_z[i]);
+    cudaStream_t st = (v->n_sub == 1) ? v->stream : v->sub_stream[i];
+    if (v->n_sub > 1) CK(cudaStreamWaitEvent(st, v->ev_ready[slot], 0));
+    CK(tsdf::launch_integrate(q, st));
+    CK(cudaEventRecord(v->ev_join[slot][i], st));
+    v->stats.kernel_launches += 1;
+  }
+  v->slot_busy[slot] = true;
+  v->last_slot = slot;
   v->stats.frames_integrated += n;
   v->n_points = -1;
+  return TSDF_OK;
+}
+
+// v->stream (and through it every later API call) waits for the sub-slab kernels launched so far.
+int join_substreams(tsdf_volume* v) {
+  if (v->n_sub > 1 && v->last_slot >= 0)
+    for (int i = 0; i < v->n_sub; ++i) CK(cudaStreamWaitEvent(v->stream, v->ev_join[v->last_slot][i], 0));
+  return TSDF_OK;
+}
+
+// Before ring slot `slot` is overwritten: `stream` waits for the kernels that still read it.
+int wait_slot_free(tsdf_volume* v, int slot, cudaStream_t stream, bool also_host) {
+  if (!v->slot_busy[slot]) return TSDF_OK;
+  for (int i = 0; i < v->n_sub; ++i) {
+    CK(cudaStreamWaitEvent(stream, v->ev_join[slot][i], 0));
+    if (also_host) CK(cudaEventSynchronize(v->ev_join[slot][i]));
+  }
   return TSDF_OK;
 }
 
@@ -144,7 +193,9 @@ int ensure_ring(tsdf_volume* v, bool u16) {
   for (int s = 0; s < kSlots; ++s) {
     if (!v->dev_depth[s]) CK(cudaMalloc(&v->dev_depth[s], px * sizeof(float)));
     if (!v->ev_copied[s]) CK(cudaEventCreateWithFlags(&v->ev_copied[s], cudaEventDisableTiming));
-    if (!v->ev_consumed[s]) CK(cudaEventCreateWithFlags(&v->ev_consumed[s], cudaEventDisableTiming));
+    if (!v->ev_ready[s]) CK(cudaEventCreateWithFlags(&v->ev_ready[s], cudaEventDisableTiming));
+    for (int i = 0; i < kMaxSub; ++i)
+      if (!v->ev_join[s][i]) CK(cudaEventCreateWithFlags(&v->ev_join[s][i], cudaEventDisableTiming));
     if (u16 && !v->dev_mm[s]) CK(cudaMalloc(&v->dev_mm[s], px * sizeof(uint16_t)));
   }
   if (!v->copy_stream) CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
@@ -186,11 +237,8 @@ int integrate_from_host(tsdf_volume* v, int n_frames, const Src* src, const floa
     const int s = (int)(v->ring_pos++ % kSlots);
     const size_t elems = (size_t)n * v->frame_px;
     const Src* chunk = src + (size_t)f0 * v->frame_px;
-    if (v->slot_busy[s]) {
-      // the pinned staging buffer and the device slot are reused: wait for their last consumer
-      if (kind == MemKind::PageableHost) CK(cudaEventSynchronize(v->ev_consumed[s]));
-      CK(cudaStreamWaitEvent(v->copy_stream, v->ev_consumed[s], 0));
-    }
+    // the pinned staging buffer and the device slot are reused: wait for their last consumers
+    if ((rc = wait_slot_free(v, s, v->copy_stream, kind == MemKind::PageableHost))) return rc;
     const void* from = chunk;
     if (kind == MemKind::PageableHost) {
       void* pin = u16 ? (void*)v->pin_mm[s] : (void*)v->pin_depth[s];
@@ -207,12 +255,10 @@ int integrate_from_host(tsdf_volume* v, int n_frames, const Src* src, const floa
     else
       CK(tsdf::launch_sanitize_depth(v->dev_depth[s], v->dev_depth[s], (int64_t)elems, v->stream));
     v->stats.kernel_launches += 1;
-    rc = launch_chunk(v, v->dev_depth[s], cam2base + 16 * (size_t)f0, n);
+    rc = launch_chunk(v, s, cam2base + 16 * (size_t)f0, n);
     if (rc) return rc;
-    CK(cudaEventRecord(v->ev_consumed[s], v->stream));
-    v->slot_busy[s] = true;
   }
-  return TSDF_OK;
+  return join_substreams(v);
 }
 
 }  // namespace
@@ -284,6 +330,18 @@ int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
       return fail(set_err(TSDF_ERR_CUDA, "cudaMalloc of %lld voxels: %s", (long long)v->n_vox, cudaGetErrorString(e)));
     v->owns_volume = true;
   }
+  {
+    // sub-slabs: cut at multiples of 8 planes (the z extent of a thread's voxel patch)
+    int want = (v->tuning >> 10) & 3;
+    if (want == 0) want = 2;
+    if (v->nz < 64) want = 1;
+    v->n_sub = want;
+    for (int i = 0; i <= want; ++i) v->sub_z[i] = (i == want) ? v->nz : ((v->nz * i / want) / 8) * 8;
+    for (int i = 0; i < want && want > 1; ++i) {
+      e = cudaStreamCreateWithFlags(&v->sub_stream[i], cudaStreamNonBlocking);
+      if (e != cudaSuccess) return fail(set_err(TSDF_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)));
+    }
+  }
   e = cudaEventCreate(&v->t0);
   if (e == cudaSuccess) e = cudaEventCreate(&v->t1);
   if (e != cudaSuccess) return fail(set_err(TSDF_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)));
@@ -297,13 +355,17 @@ void tsdf_destroy(tsdf_volume* v) {
   cudaSetDevice(v->d.device);
   if (v->stream) cudaStreamSynchronize(v->stream);
   if (v->copy_stream) { cudaStreamSynchronize(v->copy_stream); cudaStreamDestroy(v->copy_stream); }
+  for (int i = 0; i < kMaxSub; ++i)
+    if (v->sub_stream[i]) { cudaStreamSynchronize(v->sub_stream[i]); cudaStreamDestroy(v->sub_stream[i]); }
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(v->dev_depth[s]);
     cudaFree(v->dev_mm[s]);
     if (v->pin_depth[s]) cudaFreeHost(v->pin_depth[s]);
     if (v->pin_mm[s]) cudaFreeHost(v->pin_mm[s]);
     if (v->ev_copied[s]) cudaEventDestroy(v->ev_copied[s]);
-    if (v->ev_consumed[s]) cudaEventDestroy(v->ev_consumed[s]);
+    if (v->ev_ready[s]) cudaEventDestroy(v->ev_ready[s]);
+    for (int i = 0; i < kMaxSub; ++i)
+      if (v->ev_join[s][i]) cudaEventDestroy(v->ev_join[s][i]);
   }
   if (v->owns_volume) { cudaFree(v->tsdf); cudaFree(v->weight); }
   cudaFree(v->tile_offsets);
@@ -374,13 +436,14 @@ int tsdf_integrate_batch(tsdf_volume* v, int32_t n_frames, const float* depth_fr
     for (int f0 = 0; f0 < n_frames; f0 += v->batch) {
       const int n = (n_frames - f0 < v->batch) ? n_frames - f0 : v->batch;
       const int s = (int)(v->ring_pos++ % kSlots);
+      if (int rc = wait_slot_free(v, s, v->stream, false)) return rc;
       // the caller's frames stay untouched: invalid pixels are marked in the engine's own copy
       CK(tsdf::launch_sanitize_depth(depth_frames + (size_t)f0 * v->frame_px, v->dev_depth[s], (int64_t)n * v->frame_px,
                                      v->stream));
       v->stats.kernel_launches += 1;
-      if (int rc = launch_chunk(v, v->dev_depth[s], cam2base + 16 * (size_t)f0, n)) return rc;
+      if (int rc = launch_chunk(v, s, cam2base + 16 * (size_t)f0, n)) return rc;
     }
-    return TSDF_OK;
+    return join_substreams(v);
   }
   return integrate_from_host<float>(v, n_frames, depth_frames, cam2base, kind);
 }
@@ -395,12 +458,13 @@ int tsdf_integrate_batch_u16(tsdf_volume* v, int32_t n_frames, const uint16_t* d
     for (int f0 = 0; f0 < n_frames; f0 += v->batch) {
       const int n = (n_frames - f0 < v->batch) ? n_frames - f0 : v->batch;
       const int s = (int)(v->ring_pos++ % kSlots);
+      if (int rc = wait_slot_free(v, s, v->stream, false)) return rc;
       CK(tsdf::launch_depth_from_u16(depth_mm + (size_t)f0 * v->frame_px, v->dev_depth[s], (int64_t)n * v->frame_px,
                                      true, v->stream));
       v->stats.kernel_launches += 1;
-      if (int rc = launch_chunk(v, v->dev_depth[s], cam2base + 16 * (size_t)f0, n)) return rc;
+      if (int rc = launch_chunk(v, s, cam2base + 16 * (size_t)f0, n)) return rc;
     }
-    return TSDF_OK;
+    return join_substreams(v);
   }
   return integrate_from_host<uint16_t>(v, n_frames, depth_mm, cam2base, kind);
 }

@@ -195,7 +195,8 @@ integrate_kernel(const __grid_constant__ IntegrateParams P, const float* __restr
   const int rows_per_block = kBlockThreads >> P.lx_shift;
   const int xu = (blockIdx.x << P.lx_shift) + lx;
   const int y = blockIdx.y * rows_per_block + ly;
-  const int zl0 = blockIdx.z * ZT;
+  // z groups are dispatched heaviest first (far planes see more of the frustum) to shorten the tail
+  const int zl0 = (P.z_reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z) * ZT;
   const bool active = (xu < P.nx_units) && (y < P.dim_y);
   const int zcount = min(ZT, P.nz - zl0);
 
@@ -405,7 +406,8 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
   const int rows_per_block = kBlockThreads >> P.lx_shift;
   const int xu = (blockIdx.x << P.lx_shift) + lx;
   const int y = blockIdx.y * rows_per_block + ly;
-  const int zl0 = blockIdx.z * ZT;
+  // z groups are dispatched heaviest first (far planes see more of the frustum) to shorten the tail
+  const int zl0 = (P.z_reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z) * ZT;
   const bool active = (xu < P.nx_units) && (y < P.dim_y);
   const int zcount = min(ZT, P.nz - zl0);
 

@@ -164,11 +164,41 @@ def run_ours(args):
     if args.frames:
         cfg["frames"] = args.frames
     grid, F = cfg["grid"], cfg["frames"]
-    z0, z1 = pkg.sharding.slab_range(grid.dims[2], rank, world)
     depth, poses = build_inputs(pkg, cfg, device, rank, world, dist)
+    # z-slabs of equal cost (near planes see little of the frustum): the analytic frustum estimate gives
+    # the first partition, then --rebalance warm-up steps feed the measured rank times back into it.
+    # --equal-slabs: equal height.
+    def make_volume(z_range):
+        return pkg.Volume(grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin, synth.CAM_K, z_range=z_range,
+                          device=local_rank, max_batch=args.batch, cull_level=args.cull, tuning=args.tuning)
 
-    vol = pkg.Volume(grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin, synth.CAM_K, z_range=(z0, z1),
-                     device=local_rank, max_batch=args.batch, cull_level=args.cull, tuning=args.tuning)
+    plane_cost, ranges = None, [pkg.sharding.slab_range(grid.dims[2], r, world) for r in range(world)]
+    if world > 1 and not args.equal_slabs:
+        plane_cost = pkg.sharding.estimate_plane_cost(grid.dims, grid.origin, grid.voxel_size, synth.CAM_K, poses)
+        ranges = pkg.sharding.weighted_slab_ranges(plane_cost, world)
+    vol = make_volume(ranges[rank])
+    rebalance_log = []
+    if plane_cost is not None:
+        for _ in range(args.rebalance):
+            vol.reset()
+            vol.synchronize()
+            barrier()
+            vol.timer_start()
+            vol.integrate_batch(depth, poses)
+            t = torch.tensor([vol.timer_stop()], dtype=torch.float64, device=device)
+            gathered = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(gathered, t)
+            rank_t = [float(g.item()) for g in gathered]
+            rebalance_log.append([round(x, 1) for x in rank_t])
+            if max(rank_t) / (sum(rank_t) / world) < 1.02:
+                break
+            plane_cost = pkg.sharding.refine_plane_cost(plane_cost, ranges, rank_t)
+            new_ranges = pkg.sharding.weighted_slab_ranges(plane_cost, world)
+            if new_ranges[rank] != ranges[rank]:
+                vol.close()
+                vol = make_volume(new_ranges[rank])
+            ranges = new_ranges
+    z0, z1 = ranges[rank]
     slab_voxels = vol.n_voxels
     total_voxels = grid.n_voxels
 
@@ -180,9 +210,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local_rank)   # every rank watches its own GPU
+    sampler.start()
     vol.reset_stats()
     barrier()
     vol.timer_start()
@@ -190,7 +219,20 @@ def run_ours(args):
         step_device()
     ms = vol.timer_stop()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    rank_ms = [ms / args.steps]
+    if world > 1:
+        gathered = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([ms / args.steps], dtype=torch.float64, device=device))
+        rank_ms = [round(float(g.item()), 2) for g in gathered]
+    clocks = sampler.stop()
+    if world > 1:
+        mhz = torch.tensor([clocks["sm_mhz"] or 0.0], dtype=torch.float64, device=device)
+        all_mhz = [torch.zeros_like(mhz) for _ in range(world)]
+        dist.all_gather(all_mhz, mhz)
+        flags = torch.tensor([float(any(r != "sw_power_cap" for r in clocks["reasons"]))], dtype=torch.float64, device=device)
+        dist.all_reduce(flags, op=dist.ReduceOp.SUM)
+        clocks["rank_sm_mhz"] = [float(m.item()) for m in all_mhz]
+        clocks["ranks_with_slowdown_reasons"] = int(flags.item())
     launches = sum_over_ranks(vol.stats()["kernel_launches"])
     ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
@@ -200,7 +242,9 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "ms_per_step": round(ms_per_step, 3),
                               "config_key": args.config, "frames": F, "batch": args.batch, "cull": args.cull,
-                              "tuning": args.tuning, "clocks": clocks, "quick": True}), flush=True)
+                              "tuning": args.tuning, "slab_rank0": [int(z0), int(z1)], "rank_ms": rank_ms, "rebalance": rebalance_log, "clocks": clocks,
+                              "quick": True}),
+                  flush=True)
         vol.close()
         if world > 1:
             dist.destroy_process_group()
@@ -298,7 +342,9 @@ def run_ours(args):
                                    f"K={args.batch} frames per pass, z-slab sharded over {world} GPU(s)",
                        "config_key": args.config, "frames": F, "batch": args.batch, "cull_level": args.cull,
                        "l2": "volume (>= 1 GB per GPU) is larger than L2; no flush needed",
-                       "parallelism": f"z-slab x{world}"},
+                       "parallelism": f"z-slab x{world}" + ("" if world == 1 else (" equal-height" if args.equal_slabs else " equal-cost (feedback-balanced)")),
+                       "slabs": [list(map(int, r)) for r in ranges], "rank_ms_per_step": rank_ms,
+                       "rebalance_warmup_ms": rebalance_log},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_k1": roofline_k1,
             "cpu_baseline": cpu, "clocks": clocks,
         }
@@ -413,6 +459,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="value only: skip e2e, K=1 roofline and CPU baseline")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--equal-slabs", action="store_true", help="equal-height z-slabs instead of equal-cost ones")
+    ap.add_argument("--rebalance", type=int, default=3, help="feedback-balancing warm-up steps for N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

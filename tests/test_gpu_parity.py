@@ -64,10 +64,12 @@ def test_batching_and_culling_do_not_change_bits(pkg, sequence):
     depth, _, poses, K = sequence(frames)
     dims, voxel, trunc = (256, 256, 256), 0.012, 0.06
     base = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=1, cull_level=0)
-    for batch, cull in [(1, 2), (8, 0), (16, 2), (32, 1), (5, 2)]:
-        got = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=batch, cull_level=cull)
+    # tuning bits 10-11: number of concurrent sub-slab streams (1..3), bit 9: z dispatch order
+    for batch, cull, tuning in [(1, 2, 0), (8, 0, 1 << 10), (16, 2, 3 << 10), (32, 1, 0), (5, 2, 512), (7, 2, 2 << 10)]:
+        got = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=batch, cull_level=cull,
+                       tuning=tuning)
         for a, b, name in zip(got, base, ("tsdf", "weight", "points")):
-            assert_bit_equal(a, b, f"{name} K={batch} cull={cull}")
+            assert_bit_equal(a, b, f"{name} K={batch} cull={cull} tuning={tuning}")
 
 
 def test_fast_classification_equals_exact_path(pkg, sequence):
