@@ -122,6 +122,7 @@ void fill_params(const tsdf_volume* v, tsdf::IntegrateParams* p) {
   p->fast_level = (v->tuning & 0x100) ? 0 : 1;
   p->variant = v->tuning & 0xff;
   p->force_lx = (v->tuning >> 12) & 0xff;
+  p->no_ptx = (v->tuning >> 20) & 1;
 }
 
 void pose_from_cam2base(const float* c, tsdf::FramePose* o) {

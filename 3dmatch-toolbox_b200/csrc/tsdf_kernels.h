@@ -36,6 +36,7 @@ struct IntegrateParams {
   float cull_gx, cull_gy, cull_z;  // conservative margins (see make_cull_margins)
   int fast_level;        // 0: every voxel through the exact path, 1: fast classification first
   int variant;           // tuning variant of the kernel instantiation (0 = production)
+  int no_ptx;            // validation: use the C++ classification instead of the PTX block
   int z_reverse;         // dispatch the z groups of the slab in descending order
   int force_lx;          // tuning: threads of a warp laid along x (0 = choose by lane waste)
   int sanitized;         // depth frames went through sanitize_depth_kernel (invalid = -inf)
