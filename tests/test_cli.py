@@ -119,3 +119,47 @@ def test_cli_real_sample_frame(pkg, oracle, tmp_path):
     assert (tmp_path / "tsdf.ply").read_bytes() == (tmp_path / "oracle.ply").read_bytes()
     raw = np.fromfile(tmp_path / "tsdf.bin", np.float32)
     assert np.array_equal(raw[8:].view(np.uint32), t.ravel().view(np.uint32))
+
+
+def test_fuse_fragments_matches_per_fragment_demo(pkg, oracle, synth, tmp_path):
+    """Native fragment driver (fuseSceneFragments.m:36-81): every cloud_bin_N.ply equals the tsdf.ply of
+    `demo camK seq f f 50 ...` on the same window; info files carry scene, sequence, frame range, base pose."""
+    import cv2
+    frag = 12  # frames per fragment (the script's numFramesPerFrag, 50, shortened to keep the test small)
+    data, out = tmp_path / "data", tmp_path / "fragments"
+    K = synth.CAM_K.copy()
+    K[[0, 2, 4, 5]] *= np.float32(0.25)
+    n_per_seq = {"seq-01": 40, "seq-02": 27}
+    (data / "scene-a").mkdir(parents=True)
+    write_matrix(data / "scene-a" / "camera-intrinsics.txt", K.reshape(3, 3))
+    for seq, n in n_per_seq.items():
+        d = data / "scene-a" / seq
+        d.mkdir()
+        start = 0 if seq == "seq-01" else 300
+        frames = [start + 3 * i for i in range(n)]
+        mm = synth.mm_to_u16_numpy(synth.render_depth_mm(frames, im_size=(160, 120), cam_K=K))
+        c2w, _ = synth.make_poses(frames)
+        for i in range(n):
+            assert cv2.imwrite(str(d / f"frame-{i:06d}.depth.png"), mm[i])
+            write_matrix(d / f"frame-{i:06d}.pose.txt", c2w[i])
+    tool = ROOT / "3dmatch-toolbox_b200" / "bin" / "fuse_fragments"
+    common = ["--image", "160", "120", "--dim", "80", "--batch", "5"]
+    run = subprocess.run([str(tool), str(data), str(out), "--frames", str(frag), "--voxel", "0.0375", *common],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    # windows: f = 0:frag:(n-1-frag)  -> seq-01 (40 frames): 0, 12, 24; seq-02 (27 frames): 0, 12
+    expected = [("seq-01", 0), ("seq-01", 12), ("seq-01", 24), ("seq-02", 0), ("seq-02", 12)]
+    assert sorted(p.name for p in (out / "scene-a").glob("*.ply")) == [f"cloud_bin_{i}.ply" for i in range(5)]
+    for idx, (seq, first) in enumerate(expected):
+        work = tmp_path / f"demo_{idx}"
+        work.mkdir()
+        argv = [str(DEMO), str(data / "scene-a" / "camera-intrinsics.txt"), str(data / "scene-a" / seq), str(first),
+                str(first), str(frag), "-1.5", "-1.5", "0.5", "0.0375", "%f" % (0.0375 * 5), *common]
+        assert subprocess.run(argv, cwd=work, capture_output=True, timeout=300).returncode == 0
+        assert (work / "tsdf.ply").read_bytes() == (out / "scene-a" / f"cloud_bin_{idx}.ply").read_bytes()
+        info = (out / "scene-a" / f"cloud_bin_{idx}.info.txt").read_text().splitlines()
+        assert info[0] == f"scene-a\t {seq}\t {first}\t {first + frag - 1}\t"
+        pose = np.loadtxt(data / "scene-a" / seq / f"frame-{first:06d}.pose.txt")
+        assert info[1] == "".join("%15.8e\t " % v for v in pose[0]).rstrip(" ")
+        assert len(info) == 5
+    assert len(np.frombuffer((out / "scene-a" / "cloud_bin_0.ply").read_bytes().split(b"end_header\n")[1], np.float32)) > 300
