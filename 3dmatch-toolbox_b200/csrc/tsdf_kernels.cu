@@ -453,11 +453,12 @@ __device__ __forceinline__ void apply_pending(float& t, float& w, unsigned c) {
   }
 }
 
-template <int VEC, int ZT, bool DEVPOSE, int MINB, bool SANITIZED, bool USE_PTX>
+template <int VEC, int ZT, bool DEVPOSE, int MINB, bool SANITIZED, bool USE_PTX, int ROLL>
 __global__ void __launch_bounds__(kBlockThreads, MINB)
 integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float* __restrict__ d_cam_K,
                          const float* __restrict__ d_cam2base) {
   static_assert(VEC == 4 || VEC == 1, "VEC");
+  static_assert(VEC * ZT <= 32, "one bit of the exact mask per voxel of the patch");
   const int lx_mask = (1 << P.lx_shift) - 1;
   const int lx = threadIdx.x & lx_mask;
   const int ly = threadIdx.x >> P.lx_shift;
@@ -516,9 +517,20 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
   const float base_y = __fadd_rn(P.oy, __fmul_rn((float)y, P.voxel_size));  // demo.cu:31
   const int64_t plane = (int64_t)P.dim_y * P.dim_x;
   const int64_t idx0 = (int64_t)zl0 * plane + (int64_t)y * P.dim_x + (int64_t)xu * VEC;
-  unsigned pend[ZT];  // byte j of pend[k]: pending free-space updates of voxel (j, k)
+  // byte j of pend(k): pending free-space updates of voxel (j, k).  ROLL == 0: ZT registers and fully
+  // unrolled plane loops (32 inlined voxel bodies, ~20 KB of code per frame iteration).  ROLL > 0: the
+  // counts live in shared memory, which can be indexed dynamically, so the plane loop is unrolled only ROLL
+  // times and the hot loop fits the instruction cache.
+  constexpr bool kRolled = ROLL > 0;
+  __shared__ unsigned s_pend[kRolled ? ZT : 1][kRolled ? kBlockThreads : 1];
+  unsigned pend_reg[kRolled ? 1 : ZT];
+  if constexpr (kRolled) {
 #pragma unroll
-  for (int k = 0; k < ZT; ++k) pend[k] = 0u;
+    for (int k = 0; k < ZT; ++k) s_pend[k][threadIdx.x] = 0u;
+  } else {
+#pragma unroll
+    for (int k = 0; k < ZT; ++k) pend_reg[k] = 0u;
+  }
 
   for (unsigned fm = frame_mask; fm != 0u; fm &= fm - 1u) {
     const int f = __ffs(fm) - 1;
@@ -539,27 +551,37 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
 
     unsigned exact = 0u;  // bit k*VEC + j: voxel needs voxel_observation_exact
     if (active) {
+      auto plane_body = [&](int k, unsigned& pk) {
+        const float t2 = __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), ps.tz);
+        const float zx = __fmul_rn(ps.m8, t2), zy = __fmul_rn(ps.m9, t2), zz = __fmul_rn(ps.m10, t2);
+        unsigned ex = 0u;
 #pragma unroll
-      for (int k = 0; k < ZT; ++k) {
-        if (k < zcount) {  // block-uniform: only the topmost z group of a slab is ragged
-          const float t2 =
-              __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), ps.tz);
-          const float zx = __fmul_rn(ps.m8, t2), zy = __fmul_rn(ps.m9, t2), zz = __fmul_rn(ps.m10, t2);
-#pragma unroll
-          for (int j = 0; j < VEC; ++j) {
-            if constexpr (SANITIZED && USE_PTX) {
-              voxel_classify_ptx(__fadd_rn(sx[j], zx), __fadd_rn(sy[j], zy), __fadd_rn(sz[j], zz), K, depth,
-                                 P.im_w, P.im_h, P.trunc_margin, 1u << (8 * j), 1u << (k * VEC + j), pend[k],
-                                 exact);
-            } else {
-              bool free_space, need_exact;
-              voxel_classify<SANITIZED>(__fadd_rn(sx[j], zx), __fadd_rn(sy[j], zy), __fadd_rn(sz[j], zz), K,
-                                        depth, P.im_w, P.im_h, P.trunc_margin, free_space, need_exact);
-              if (free_space) pend[k] += 1u << (8 * j);
-              if (need_exact) exact |= 1u << (k * VEC + j);
-            }
+        for (int j = 0; j < VEC; ++j) {
+          if constexpr (SANITIZED && USE_PTX) {
+            voxel_classify_ptx(__fadd_rn(sx[j], zx), __fadd_rn(sy[j], zy), __fadd_rn(sz[j], zz), K, depth, P.im_w,
+                               P.im_h, P.trunc_margin, 1u << (8 * j), 1u << j, pk, ex);
+          } else {
+            bool free_space, need_exact;
+            voxel_classify<SANITIZED>(__fadd_rn(sx[j], zx), __fadd_rn(sy[j], zy), __fadd_rn(sz[j], zz), K, depth,
+                                      P.im_w, P.im_h, P.trunc_margin, free_space, need_exact);
+            if (free_space) pk += 1u << (8 * j);
+            if (need_exact) ex |= 1u << j;
           }
         }
+        exact |= ex << (k * VEC);
+      };
+      // block-uniform bound: only the topmost z group of a slab is ragged
+      if constexpr (kRolled) {
+#pragma unroll ROLL
+        for (int k = 0; k < zcount; ++k) {
+          unsigned pk = s_pend[k][threadIdx.x];
+          plane_body(k, pk);
+          s_pend[k][threadIdx.x] = pk;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < ZT; ++k)
+          if (k < zcount) plane_body(k, pend_reg[k]);
       }
     }
 
@@ -578,16 +600,27 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
                                                        P.im_h, P.trunc_margin);
         if (dj != kNoObservation) {
           unsigned c = 0u;
-#pragma unroll
-          for (int kk = 0; kk < ZT; ++kk)
-            if (kk == k) {
-              if (dj == 1.0f) {
-                pend[kk] += 1u << (8 * j);
-              } else {
-                c = (pend[kk] >> (8 * j)) & 0xffu;
-                pend[kk] &= ~(0xffu << (8 * j));
-              }
+          if constexpr (kRolled) {
+            unsigned pk = s_pend[k][threadIdx.x];
+            if (dj == 1.0f) {
+              pk += 1u << (8 * j);
+            } else {
+              c = (pk >> (8 * j)) & 0xffu;
+              pk &= ~(0xffu << (8 * j));
             }
+            s_pend[k][threadIdx.x] = pk;
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < ZT; ++kk)
+              if (kk == k) {
+                if (dj == 1.0f) {
+                  pend_reg[kk] += 1u << (8 * j);
+                } else {
+                  c = (pend_reg[kk] >> (8 * j)) & 0xffu;
+                  pend_reg[kk] &= ~(0xffu << (8 * j));
+                }
+              }
+          }
           if (dj != 1.0f) {
             // in-band observation: flush the voxel's pending free-space updates, then demo.cu:63-66
             const int64_t idx = idx0 + (int64_t)k * plane + j;
@@ -604,19 +637,25 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
   }
 
   // ---- write-back of the pending free-space counts: coalesced, warp-uniform per plane ----
-#pragma unroll
-  for (int k = 0; k < ZT; ++k) {
-    if (__any_sync(0xffffffffu, pend[k] != 0u)) {
+  auto write_back = [&](int k, unsigned pk) {
+    if (__any_sync(0xffffffffu, pk != 0u)) {
       if (active && k < zcount) {
         float T[VEC], W[VEC];
         Row<VEC>::load(P.tsdf + idx0 + k * plane, T);
         Row<VEC>::load(P.weight + idx0 + k * plane, W);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) apply_pending(T[j], W[j], (pend[k] >> (8 * j)) & 0xffu);
+        for (int j = 0; j < VEC; ++j) apply_pending(T[j], W[j], (pk >> (8 * j)) & 0xffu);
         Row<VEC>::store(P.tsdf + idx0 + k * plane, T);
         Row<VEC>::store(P.weight + idx0 + k * plane, W);
       }
     }
+  };
+  if constexpr (kRolled) {
+#pragma unroll 1
+    for (int k = 0; k < ZT; ++k) write_back(k, s_pend[k][threadIdx.x]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < ZT; ++k) write_back(k, pend_reg[k]);
   }
 }
 
@@ -805,7 +844,7 @@ int ilog2(int v) {
   return s;
 }
 
-template <int VEC, int ZT, bool DEVPOSE, int MINB, bool FAST = true, bool PENDING = false>
+template <int VEC, int ZT, bool DEVPOSE, int MINB, bool FAST = true, bool PENDING = false, int ROLL = 0>
 cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float* d_pose, cudaStream_t s) {
   p.nx_units = p.dim_x / VEC;
   p.lim_x = 0.5f - pixel_round_margin((float)p.im_w, p.cx);
@@ -827,14 +866,14 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
             (unsigned)((p.nz + ZT - 1) / ZT));
   if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
   if (FAST && (p.fast_level == 0 || !(p.trunc_margin > 0.0f)))
-    return launch_integrate_t<VEC, ZT, DEVPOSE, MINB, false, false>(p, d_K, d_pose, s);
+    return launch_integrate_t<VEC, ZT, DEVPOSE, MINB, false, false, 0>(p, d_K, d_pose, s);
   if constexpr (PENDING) {
     if (p.sanitized && !p.no_ptx)
-      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, true><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, true, ROLL><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
     else if (p.sanitized)
-      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, false><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, false, ROLL><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
     else
-      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, false, false><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, false, false, ROLL><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
   }
   else
     integrate_kernel<VEC, ZT, DEVPOSE, MINB, FAST><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
@@ -845,7 +884,7 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
 
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
   if (p.n_frames < 1 || p.n_frames > kMaxBatch) return cudaErrorInvalidValue;
-  if (p.dim_x % 4 != 0) return launch_integrate_t<1, 4, false, 4, true, true>(p, nullptr, nullptr, s);
+  if (p.dim_x % 4 != 0) return launch_integrate_t<1, 8, false, 5, true, true, 2>(p, nullptr, nullptr, s);
   switch (p.variant) {  // tuning variants (tsdf_volume_desc.reserved0); 0 is the production choice
     case 1: return launch_integrate_t<4, 4, false, 2>(p, nullptr, nullptr, s);
     case 2: return launch_integrate_t<4, 4, false, 3>(p, nullptr, nullptr, s);
@@ -858,7 +897,12 @@ cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
     case 9: return launch_integrate_t<4, 8, false, 3, true, true>(p, nullptr, nullptr, s);
     case 10: return launch_integrate_t<4, 4, false, 6, true, true>(p, nullptr, nullptr, s);
     case 11: return launch_integrate_t<4, 8, false, 4, true, true>(p, nullptr, nullptr, s);
-    default: return launch_integrate_t<4, 8, false, 5, true, true>(p, nullptr, nullptr, s);
+    case 12: return launch_integrate_t<4, 8, false, 5, true, true, 1>(p, nullptr, nullptr, s);
+    case 13: return launch_integrate_t<4, 8, false, 5, true, true, 2>(p, nullptr, nullptr, s);
+    case 14: return launch_integrate_t<4, 8, false, 6, true, true, 2>(p, nullptr, nullptr, s);
+    case 16: return launch_integrate_t<4, 8, false, 5, true, true, 4>(p, nullptr, nullptr, s);
+    case 17: return launch_integrate_t<4, 8, false, 5, true, true>(p, nullptr, nullptr, s);
+    default: return launch_integrate_t<4, 8, false, 5, true, true, 2>(p, nullptr, nullptr, s);
   }
 }
 
@@ -870,8 +914,8 @@ cudaError_t launch_integrate_devpose(IntegrateParams p, const float* d_cam_K, co
   p.sanitized = 0;   // the caller's depth image is read in place
   const bool vec4 = (p.dim_x % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.tsdf) & 15u) == 0) &&
                     ((reinterpret_cast<uintptr_t>(p.weight) & 15u) == 0);
-  if (vec4) return launch_integrate_t<4, 4, true, 4, true, true>(p, d_cam_K, d_cam2base, s);
-  return launch_integrate_t<1, 4, true, 4, true, true>(p, d_cam_K, d_cam2base, s);
+  if (vec4) return launch_integrate_t<4, 8, true, 5, true, true, 2>(p, d_cam_K, d_cam2base, s);
+  return launch_integrate_t<1, 8, true, 5, true, true, 2>(p, d_cam_K, d_cam2base, s);
 }
 
 cudaError_t launch_fill(float* tsdf, float* weight, int64_t n, cudaStream_t s) {
