@@ -453,7 +453,9 @@ __device__ __forceinline__ void apply_pending(float& t, float& w, unsigned c) {
   }
 }
 
-template <int VEC, int ZT, bool DEVPOSE, int MINB, bool SANITIZED, bool USE_PTX, int ROLL>
+constexpr int kExactQueueCap = 256;  // exact-evaluation queue entries per warp
+
+template <int VEC, int ZT, bool DEVPOSE, int MINB, bool SANITIZED, bool USE_PTX, int ROLL, bool QUEUE>
 __global__ void __launch_bounds__(kBlockThreads, MINB)
 integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float* __restrict__ d_cam_K,
                          const float* __restrict__ d_cam2base) {
@@ -523,6 +525,7 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
   // times and the hot loop fits the instruction cache.
   constexpr bool kRolled = ROLL > 0;
   __shared__ unsigned s_pend[kRolled ? ZT : 1][kRolled ? kBlockThreads : 1];
+  __shared__ unsigned short s_queue[(QUEUE && kRolled) ? kBlockThreads / 32 : 1][(QUEUE && kRolled) ? kExactQueueCap : 1];
   unsigned pend_reg[kRolled ? 1 : ZT];
   if constexpr (kRolled) {
 #pragma unroll
@@ -585,7 +588,74 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
       }
     }
 
-    // ---- compacted exact evaluations: every lane pops its own pending voxels ----
+    // ---- exact evaluations, redistributed over the warp: the voxels that need the exact path are few
+    //      and unevenly spread (a surface band crossing the tile hits 2-3 lanes with up to 32 voxels each),
+    //      so they are queued in shared memory and handed out one per lane; results go back to the owner's
+    //      pending counts through shared-memory atomics, in-band ones are applied by the lane that computed
+    //      them.  Frame order per voxel is kept: the queue is drained before the next frame starts.
+    if constexpr (QUEUE && kRolled) {
+      const unsigned lane = threadIdx.x & 31u;
+      const unsigned n_mine = __popc(exact);
+      unsigned incl = n_mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+      }
+      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total != 0u && total <= (unsigned)kExactQueueCap) {  // warp-uniform
+        unsigned short* q = s_queue[threadIdx.x >> 5];
+        unsigned pos = incl - n_mine;
+        while (exact != 0u) {
+          const unsigned s = (unsigned)(__ffs(exact) - 1);
+          exact &= exact - 1u;
+          q[pos++] = (unsigned short)(lane | (s << 5));
+        }
+        __syncwarp();
+        for (unsigned base = 0; base < total; base += 32u) {
+          const unsigned i = base + lane;
+          if (i < total) {
+            const unsigned item = q[i];
+            const int owner_t = (int)((threadIdx.x & ~31u) | (item & 31u));
+            const int s = (int)(item >> 5), j = s & (VEC - 1), k = s / VEC;
+            const int o_xu = (blockIdx.x << P.lx_shift) + (owner_t & lx_mask);
+            const int o_y = blockIdx.y * rows_per_block + (owner_t >> P.lx_shift);
+            // the owner's arithmetic, operation for operation (demo.cu:30-41)
+            const float q0 = __fsub_rn(__fadd_rn(P.ox, __fmul_rn((float)(o_xu * VEC + j), P.voxel_size)), ps.tx);
+            const float q1 = __fsub_rn(__fadd_rn(P.oy, __fmul_rn((float)o_y, P.voxel_size)), ps.ty);
+            const float q2 =
+                __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), ps.tz);
+            const float cam_x =
+                __fadd_rn(__fadd_rn(__fmul_rn(ps.m0, q0), __fmul_rn(ps.m4, q1)), __fmul_rn(ps.m8, q2));
+            const float cam_y =
+                __fadd_rn(__fadd_rn(__fmul_rn(ps.m1, q0), __fmul_rn(ps.m5, q1)), __fmul_rn(ps.m9, q2));
+            const float cam_z =
+                __fadd_rn(__fadd_rn(__fmul_rn(ps.m2, q0), __fmul_rn(ps.m6, q1)), __fmul_rn(ps.m10, q2));
+            const float dj = voxel_observation_exact<true>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy, depth,
+                                                           P.im_w, P.im_h, P.trunc_margin);
+            if (dj != kNoObservation) {
+              unsigned* pw = &s_pend[k][owner_t];
+              if (dj == 1.0f) {
+                atomicAdd(pw, 1u << (8 * j));
+              } else {
+                const unsigned old = atomicAnd(pw, ~(0xffu << (8 * j)));
+                const int64_t idx =
+                    ((int64_t)(zl0 + k) * P.dim_y + o_y) * (int64_t)P.dim_x + (int64_t)o_xu * VEC + j;
+                float t = P.tsdf[idx], w = P.weight[idx];
+                apply_pending(t, w, (old >> (8 * j)) & 0xffu);
+                const float w_new = __fadd_rn(w, 1.0f);
+                t = __fdiv_rn(__fadd_rn(__fmul_rn(t, w), dj), w_new);
+                P.tsdf[idx] = t;
+                P.weight[idx] = w_new;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- (remaining) exact evaluations: every lane pops its own pending voxels ----
     while (__any_sync(0xffffffffu, exact != 0u)) {
       if (exact != 0u) {
         const int s = __ffs(exact) - 1;
@@ -844,7 +914,8 @@ int ilog2(int v) {
   return s;
 }
 
-template <int VEC, int ZT, bool DEVPOSE, int MINB, bool FAST = true, bool PENDING = false, int ROLL = 0>
+template <int VEC, int ZT, bool DEVPOSE, int MINB, bool FAST = true, bool PENDING = false, int ROLL = 0,
+          bool QUEUE = false>
 cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float* d_pose, cudaStream_t s) {
   p.nx_units = p.dim_x / VEC;
   p.lim_x = 0.5f - pixel_round_margin((float)p.im_w, p.cx);
@@ -866,14 +937,14 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
             (unsigned)((p.nz + ZT - 1) / ZT));
   if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
   if (FAST && (p.fast_level == 0 || !(p.trunc_margin > 0.0f)))
-    return launch_integrate_t<VEC, ZT, DEVPOSE, MINB, false, false, 0>(p, d_K, d_pose, s);
+    return launch_integrate_t<VEC, ZT, DEVPOSE, MINB, false, false, 0, false>(p, d_K, d_pose, s);
   if constexpr (PENDING) {
     if (p.sanitized && !p.no_ptx)
-      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, true, ROLL><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, true, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
     else if (p.sanitized)
-      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, false, ROLL><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, false, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
     else
-      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, false, false, ROLL><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, false, false, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
   }
   else
     integrate_kernel<VEC, ZT, DEVPOSE, MINB, FAST><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
@@ -884,7 +955,7 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
 
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
   if (p.n_frames < 1 || p.n_frames > kMaxBatch) return cudaErrorInvalidValue;
-  if (p.dim_x % 4 != 0) return launch_integrate_t<1, 8, false, 5, true, true, 2>(p, nullptr, nullptr, s);
+  if (p.dim_x % 4 != 0) return launch_integrate_t<1, 8, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
   switch (p.variant) {  // tuning variants (tsdf_volume_desc.reserved0); 0 is the production choice
     case 1: return launch_integrate_t<4, 4, false, 2>(p, nullptr, nullptr, s);
     case 2: return launch_integrate_t<4, 4, false, 3>(p, nullptr, nullptr, s);
@@ -902,7 +973,10 @@ cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
     case 14: return launch_integrate_t<4, 8, false, 6, true, true, 2>(p, nullptr, nullptr, s);
     case 16: return launch_integrate_t<4, 8, false, 5, true, true, 4>(p, nullptr, nullptr, s);
     case 17: return launch_integrate_t<4, 8, false, 5, true, true>(p, nullptr, nullptr, s);
-    default: return launch_integrate_t<4, 8, false, 5, true, true, 2>(p, nullptr, nullptr, s);
+    case 18: return launch_integrate_t<4, 8, false, 5, true, true, 2, true>(p, nullptr, nullptr, s);
+    case 19: return launch_integrate_t<4, 8, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
+    case 20: return launch_integrate_t<4, 8, false, 5, true, true, 2>(p, nullptr, nullptr, s);
+    default: return launch_integrate_t<4, 8, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
   }
 }
 
@@ -914,8 +988,8 @@ cudaError_t launch_integrate_devpose(IntegrateParams p, const float* d_cam_K, co
   p.sanitized = 0;   // the caller's depth image is read in place
   const bool vec4 = (p.dim_x % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.tsdf) & 15u) == 0) &&
                     ((reinterpret_cast<uintptr_t>(p.weight) & 15u) == 0);
-  if (vec4) return launch_integrate_t<4, 8, true, 5, true, true, 2>(p, d_cam_K, d_cam2base, s);
-  return launch_integrate_t<1, 8, true, 5, true, true, 2>(p, d_cam_K, d_cam2base, s);
+  if (vec4) return launch_integrate_t<4, 8, true, 6, true, true, 2, true>(p, d_cam_K, d_cam2base, s);
+  return launch_integrate_t<1, 8, true, 6, true, true, 2, true>(p, d_cam_K, d_cam2base, s);
 }
 
 cudaError_t launch_fill(float* tsdf, float* weight, int64_t n, cudaStream_t s) {

@@ -300,14 +300,32 @@ def run_ours(args):
     pts_host = None
     e2e_steps = max(1, min(args.steps, 3))
 
+    class _DevPoints:  # torch view of the engine's surface-point buffer (CUDA array interface)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n, 3), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    gathered_pts = 0
+
     def step_e2e():
-        nonlocal pts_host
+        """tsdf_reset + tsdf_integrate_batch(HOST depth) + tsdf_extract_surface, then the output side:
+        N = 1: tsdf_copy_surface to the host; N > 1: ordered NCCL gather of the per-slab points to rank 0
+        (sharding.gather_surface) and the D2H copy of the assembled cloud there."""
+        nonlocal pts_host, gathered_pts
         vol.reset()
         vol.integrate_batch(depth_host, poses)
         n = vol.extract_surface_count()
-        if pts_host is None or pts_host.shape[0] < n:
-            pts_host = np.empty((int(n * 1.2) + 16, 3), np.float32)
-        pkg.binding._check(vol._lib.tsdf_copy_surface(vol._h, pts_host.ctypes.data, pts_host.shape[0]), "copy_surface")
+        if world == 1:
+            if pts_host is None or pts_host.shape[0] < n:
+                pts_host = np.empty((int(n * 1.2) + 16, 3), np.float32)
+            pkg.binding._check(vol._lib.tsdf_copy_surface(vol._h, pts_host.ctypes.data, pts_host.shape[0]), "copy_surface")
+            gathered_pts = n
+            return n
+        ptr, n_dev = vol.surface_device_ptr()
+        local = torch.as_tensor(_DevPoints(ptr, n_dev), device=device) if n_dev else torch.zeros((0, 3), dtype=torch.float32, device=device)
+        cloud = pkg.sharding.gather_surface(local, dst=0)
+        if rank == 0:
+            pts_host = cloud.cpu().numpy()
+            gathered_pts = pts_host.shape[0]
         return n
 
     step_e2e()
@@ -323,9 +341,11 @@ def run_ours(args):
     st = vol.stats()
     e2e_value = total_voxels * F / (t_e2e / e2e_steps)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st["h2d_bytes"] / e2e_steps + poses.nbytes),
-           "d2h_bytes_per_step": int(st["d2h_bytes"] / e2e_steps), "steps": e2e_steps,
-           "ms_per_step": round(t_e2e / e2e_steps * 1e3, 2), "surface_points_rank0": int(n_pts),
-           "path": "tsdf_reset + tsdf_integrate_batch(pinned host depth) + tsdf_extract_surface + tsdf_copy_surface"}
+           "d2h_bytes_per_step": int(st["d2h_bytes"] / e2e_steps) + (int(gathered_pts) * 12 if world > 1 else 0),
+           "steps": e2e_steps, "ms_per_step": round(t_e2e / e2e_steps * 1e3, 2),
+           "surface_points": int(gathered_pts),
+           "path": "tsdf_reset + tsdf_integrate_batch(pinned host depth) + tsdf_extract_surface + "
+                   + ("tsdf_copy_surface" if world == 1 else "NCCL gather of slab points to rank 0 + D2H")}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ---------------------------------------
     cpu = None
@@ -451,7 +471,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--config", default="1024", choices=["1024", "512", "demo500"])
+    ap.add_argument("--config", default="1024", choices=["1024", "512", "demo500", "2048"])
     ap.add_argument("--frames", type=int, default=0, help="override the configuration's frame count")
     ap.add_argument("--batch", type=int, default=16, help="K: frames fused per pass over the volume")
     ap.add_argument("--cull", type=int, default=2)
