@@ -50,6 +50,8 @@ struct tsdf_volume {
   bool owns_stream = false;
   // staging ring (allocated on first host-input integrate)
   float* dev_depth[kSlots] = {};
+  float* dev_mips[kSlots] = {};   // max-pyramids of the slot's frames (occlusion culling)
+  tsdf::MipLayout mip = {};
   float* pin_depth[kSlots] = {};
   uint16_t* dev_mm[kSlots] = {};
   uint16_t* pin_mm[kSlots] = {};
@@ -139,6 +141,15 @@ int launch_chunk(tsdf_volume* v, int slot, const float* cam2base, int n) {
   tsdf::IntegrateParams p;
   fill_params(v, &p);
   p.depth = v->dev_depth[slot];
+  if (v->cull >= 2) {
+    // max-pyramids of the (sanitized) frames of this slot, for the occlusion test of the frame masks
+    CK(tsdf::launch_build_depth_mips(v->dev_depth[slot], v->dev_mips[slot], n, v->d.im_width, v->d.im_height,
+                                     v->frame_px, v->stream));
+    v->stats.kernel_launches += 1;
+    p.mips = v->dev_mips[slot];
+    p.mip_stride = v->mip.stride;
+    for (int l = 0; l < 5; ++l) { p.mip_w[l] = v->mip.w[l]; p.mip_off[l] = v->mip.off[l]; }
+  }
   p.sanitized = 1;  // every depth frame reaches the kernel through sanitize / depth_from_u16(sanitize)
   p.n_frames = n;
   for (int f = 0; f < n; ++f) pose_from_cam2base(cam2base + 16 * f, &p.pose[f]);
@@ -193,6 +204,7 @@ int ensure_ring(tsdf_volume* v, bool u16) {
   const size_t px = (size_t)v->frame_px * v->batch;
   for (int s = 0; s < kSlots; ++s) {
     if (!v->dev_depth[s]) CK(cudaMalloc(&v->dev_depth[s], px * sizeof(float)));
+    if (!v->dev_mips[s]) CK(cudaMalloc(&v->dev_mips[s], (size_t)v->mip.stride * v->batch * sizeof(float)));
     if (!v->ev_copied[s]) CK(cudaEventCreateWithFlags(&v->ev_copied[s], cudaEventDisableTiming));
     if (!v->ev_ready[s]) CK(cudaEventCreateWithFlags(&v->ev_ready[s], cudaEventDisableTiming));
     for (int i = 0; i < kMaxSub; ++i)
@@ -300,6 +312,7 @@ int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
   v->nz = d.z_end - d.z_begin;
   v->n_vox = v->nz * d.dim_y * d.dim_x;
   v->frame_px = (int64_t)d.im_width * d.im_height;
+  v->mip = tsdf::make_mip_layout(d.im_width, d.im_height);
   v->batch = d.max_batch ? d.max_batch : 16;
   v->cull = (d.cull_level < 0 || d.cull_level > 2) ? 2 : d.cull_level;
   v->tuning = d.reserved0;
@@ -360,6 +373,7 @@ void tsdf_destroy(tsdf_volume* v) {
     if (v->sub_stream[i]) { cudaStreamSynchronize(v->sub_stream[i]); cudaStreamDestroy(v->sub_stream[i]); }
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(v->dev_depth[s]);
+    cudaFree(v->dev_mips[s]);
     cudaFree(v->dev_mm[s]);
     if (v->pin_depth[s]) cudaFreeHost(v->pin_depth[s]);
     if (v->pin_mm[s]) cudaFreeHost(v->pin_mm[s]);

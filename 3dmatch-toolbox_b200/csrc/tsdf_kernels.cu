@@ -213,8 +213,16 @@ struct Row<1> {
 // covers every voxel inside it.
 struct CullAccum {
   bool behind, left, right, top, bottom;
-  __device__ __forceinline__ CullAccum() : behind(true), left(true), right(true), top(true), bottom(true) {}
+  float cz_min, u_min, u_max, v_min, v_max;  // for the occlusion test (valid when cz_min > 0)
+  __device__ __forceinline__ CullAccum()
+      : behind(true), left(true), right(true), top(true), bottom(true), cz_min(INFINITY), u_min(INFINITY),
+        u_max(-INFINITY), v_min(INFINITY), v_max(-INFINITY) {}
   __device__ __forceinline__ void add(float cx, float cy, float cz, const IntegrateParams& P, const Intrinsics& K) {
+    cz_min = fminf(cz_min, cz);
+    const float inv = __fdividef(1.0f, cz);
+    const float u = fmaf(K.fx * cx, inv, K.cx), v = fmaf(K.fy * cy, inv, K.cy);
+    u_min = fminf(u_min, u); u_max = fmaxf(u_max, u);
+    v_min = fminf(v_min, v); v_max = fmaxf(v_max, v);
     // cam_z <= 0 for every voxel (demo.cu:43)
     behind = behind && (cz < -P.cull_z);
     // u = fx*cx/cz + cx0 < -2.5 (left) or > im_w + 1.5 (right) for every voxel with cam_z > 0
@@ -224,6 +232,38 @@ struct CullAccum {
     bottom = bottom && (fmaf(K.fy, cy, (K.cy - (float)P.im_h - 1.5f) * cz) > P.cull_gy);
   }
   __device__ __forceinline__ bool culled() const { return behind || left || right || top || bottom; }
+
+  // Hierarchical-Z test: true when every voxel of the hull lies at least trunc_margin BEHIND every valid
+  // depth pixel it can project to, i.e. the reference would skip all of them at demo.cu:57 (or :53).
+  //  * the hull is in front of the camera (cz_min > margin), so its projection is inside the bounding box of
+  //    the projected corners; the box is widened by 1.5 px for rounding to the nearest pixel and the
+  //    approximate divisions;
+  //  * `mips` holds, per frame, the maxima of the sanitized depth (invalid = -inf) over aligned blocks of
+  //    8..128 px; the level whose block size covers the box is read at the <= 2 x 2 blocks it touches;
+  //  * e = fl(d - cam_z) <= d_max - (cz_min - cull_z) <= -trunc * (1 + 1e-4)  =>  diff = fl(e * ray) <= -trunc
+  //    because ray >= 1.
+  __device__ __forceinline__ bool occluded(const IntegrateParams& P, const float* __restrict__ mips) const {
+    if (!(cz_min > P.cull_z + 1e-3f)) return false;
+    const float fw = (float)P.im_w, fh = (float)P.im_h;
+    if (!(u_min > -1e6f && u_max < 1e6f && v_min > -1e6f && v_max < 1e6f)) return false;
+    const int x0 = max(0, (int)floorf(u_min - 1.5f)), x1 = min(P.im_w - 1, (int)ceilf(u_max + 1.5f));
+    const int y0 = max(0, (int)floorf(v_min - 1.5f)), y1 = min(P.im_h - 1, (int)ceilf(v_max + 1.5f));
+    (void)fw; (void)fh;
+    if (x1 < x0 || y1 < y0) return true;  // projects entirely outside the image (demo.cu:48)
+    const int extent = max(x1 - x0, y1 - y0) + 1;
+    if (extent > 128) return false;
+    int level = 0;                         // index into levels 3..7 (block sizes 8..128)
+    while ((8 << level) < extent) ++level;
+    const int shift = 3 + level;
+    const int w_l = P.mip_w[level];
+    const float* m = mips + P.mip_off[level];
+    const int tx0 = x0 >> shift, tx1 = x1 >> shift, ty0 = y0 >> shift, ty1 = y1 >> shift;
+    float d_max = __ldg(m + ty0 * w_l + tx0);
+    d_max = fmaxf(d_max, __ldg(m + ty0 * w_l + tx1));
+    d_max = fmaxf(d_max, __ldg(m + ty1 * w_l + tx0));
+    d_max = fmaxf(d_max, __ldg(m + ty1 * w_l + tx1));
+    return d_max + P.trunc_margin * 1.0001f + P.cull_z <= cz_min;
+  }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -511,6 +551,8 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
                 fmaf(ps.m2, bx, fmaf(ps.m6, by, ps.m10 * bz)), P, K);
       }
       keep = !acc.culled() && (y_lo < P.dim_y);
+      if (keep && P.cull_level >= 2 && P.mips != nullptr && P.trunc_margin > 0.0f)
+        keep = !acc.occluded(P, P.mips + (int64_t)f * P.mip_stride);
     }
     frame_mask = __ballot_sync(0xffffffffu, keep);
   }
@@ -754,6 +796,51 @@ __global__ void __launch_bounds__(256) sanitize_depth_kernel(const float* __rest
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float d = in[i];
     out[i] = (d > 0.0f && d <= 6.0f) ? d : -INFINITY;
+  }
+}
+
+// Max-pyramid of sanitized depth frames for the occlusion test (CullAccum::occluded): levels 3..7, i.e. the
+// maximum over aligned blocks of 8, 16, 32, 64 and 128 pixels (pixels outside the image and invalid pixels
+// count as -inf).  One 256-thread block reduces one 128 x 128 pixel region of one frame.
+__global__ void __launch_bounds__(256) build_depth_mips_kernel(const float* __restrict__ frames, float* __restrict__ mips,
+                                                               int im_w, int im_h, int64_t frame_stride, MipLayout L) {
+  __shared__ float s[256];
+  const int frame = blockIdx.z;
+  const float* src = frames + (int64_t)frame * frame_stride;
+  float* dst = mips + (int64_t)frame * L.stride;
+  const int t = threadIdx.x;
+  // level 3: thread t owns the 8 x 8 block (bx, by) of the 16 x 16 blocks of this region; bits of t are
+  // interleaved (Morton order) so that every further 2 x 2 reduction combines 4 consecutive entries
+  int bx = 0, by = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) { bx |= ((t >> (2 * b)) & 1) << b; by |= ((t >> (2 * b + 1)) & 1) << b; }
+  const int px0 = blockIdx.x * 128 + bx * 8, py0 = blockIdx.y * 128 + by * 8;
+  float m = -INFINITY;
+  for (int yy = 0; yy < 8; ++yy) {
+    const int py = py0 + yy;
+    if (py >= im_h) break;
+    for (int xx = 0; xx < 8; ++xx) {
+      const int px = px0 + xx;
+      if (px < im_w) m = fmaxf(m, src[(int64_t)py * im_w + px]);
+    }
+  }
+  s[t] = m;
+  if (px0 < im_w && py0 < im_h) dst[L.off[0] + (py0 >> 3) * L.w[0] + (px0 >> 3)] = m;
+  __syncthreads();
+#pragma unroll
+  for (int level = 1; level < 5; ++level) {
+    const int n = 256 >> (2 * level);      // entries of this level inside the region
+    float v = -INFINITY;
+    if (t < n) v = fmaxf(fmaxf(s[4 * t], s[4 * t + 1]), fmaxf(s[4 * t + 2], s[4 * t + 3]));
+    __syncthreads();
+    if (t < n) {
+      s[t] = v;
+      int cx = 0, cy = 0;                  // de-interleave t -> block coordinates at this level
+      for (int b = 0; b < 4 - level; ++b) { cx |= ((t >> (2 * b)) & 1) << b; cy |= ((t >> (2 * b + 1)) & 1) << b; }
+      const int gx = blockIdx.x * (16 >> level) + cx, gy = blockIdx.y * (16 >> level) + cy;
+      if (gx < L.w[level] && gy < L.h[level]) dst[L.off[level] + gy * L.w[level] + gx] = v;
+    }
+    __syncthreads();
   }
 }
 
@@ -1001,6 +1088,28 @@ cudaError_t launch_fill(float* tsdf, float* weight, int64_t n, cudaStream_t s) {
 cudaError_t launch_depth_from_u16(const uint16_t* mm, float* depth, int64_t n, bool sanitize, cudaStream_t s) {
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   depth_from_u16_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(mm, depth, n, sanitize);
+  return cudaGetLastError();
+}
+
+MipLayout make_mip_layout(int im_w, int im_h) {
+  MipLayout L;
+  int off = 0;
+  for (int l = 0; l < 5; ++l) {
+    const int b = 8 << l;
+    L.w[l] = (im_w + b - 1) / b;
+    L.h[l] = (im_h + b - 1) / b;
+    L.off[l] = off;
+    off += L.w[l] * L.h[l];
+  }
+  L.stride = off;
+  return L;
+}
+
+cudaError_t launch_build_depth_mips(const float* frames, float* mips, int n_frames, int im_w, int im_h,
+                                    int64_t frame_stride, cudaStream_t s) {
+  const MipLayout L = make_mip_layout(im_w, im_h);
+  dim3 grid((unsigned)((im_w + 127) / 128), (unsigned)((im_h + 127) / 128), (unsigned)n_frames);
+  build_depth_mips_kernel<<<grid, 256, 0, s>>>(frames, mips, im_w, im_h, frame_stride, L);
   return cudaGetLastError();
 }
 

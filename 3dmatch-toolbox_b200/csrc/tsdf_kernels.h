@@ -18,6 +18,13 @@ struct FramePose {
   float tx, ty, tz;    // cam2base[3], [7], [11]
 };
 
+// Max-pyramid of a depth frame: levels 3..7 (blocks of 8..128 pixels), level l at off[l], w[l] x h[l] floats.
+struct MipLayout {
+  int w[5], h[5], off[5];
+  int stride;  // floats per frame
+};
+MipLayout make_mip_layout(int im_w, int im_h);
+
 struct IntegrateParams {
   float* tsdf;           // slab, x fastest
   float* weight;
@@ -34,6 +41,8 @@ struct IntegrateParams {
   int n_frames;          // 1..kMaxBatch
   int cull_level;        // 0 none, 1 per-thread frustum cull, 2 + per-tile frame mask
   float cull_gx, cull_gy, cull_z;  // conservative margins (see make_cull_margins)
+  const float* mips;     // max-pyramids of the batch's depth frames (nullptr = no occlusion test)
+  int mip_stride, mip_w[5], mip_off[5];
   int fast_level;        // 0: every voxel through the exact path, 1: fast classification first
   int variant;           // tuning variant of the kernel instantiation (0 = production)
   int no_ptx;            // validation: use the C++ classification instead of the PTX block
@@ -73,6 +82,8 @@ cudaError_t launch_integrate_devpose(IntegrateParams p, const float* d_cam_K, co
                                      cudaStream_t s);
 cudaError_t launch_depth_from_u16(const uint16_t* mm, float* depth, int64_t n, bool sanitize, cudaStream_t s);
 cudaError_t launch_sanitize_depth(const float* in, float* out, int64_t n, cudaStream_t s);
+cudaError_t launch_build_depth_mips(const float* frames, float* mips, int n_frames, int im_w, int im_h,
+                                    int64_t frame_stride, cudaStream_t s);
 cudaError_t launch_extract_count(const ExtractParams& p, unsigned long long* tile_counts, int64_t n_tiles,
                                  cudaStream_t s);
 cudaError_t launch_extract_scan(unsigned long long* tile_counts, int64_t n_tiles, unsigned long long* total,
