@@ -15,6 +15,8 @@
 // early-outs (demo.cu:43-49).
 #include "tsdf_kernels.h"
 
+#include <type_traits>
+
 namespace tsdf {
 
 namespace {
@@ -181,6 +183,55 @@ __device__ __forceinline__ void voxel_classify_ptx(float cam_x, float cam_y, flo
         "r"(im_w), "r"(im_h), "l"(depth), "f"(trunc_margin), "r"(pend_inc), "r"(exact_bit));
 }
 
+// The same block for "interior" tiles: the frame mask stage has shown that every voxel of the warp's tile is
+// in front of the camera and projects at least 1.5 px inside the image, so the bounds test (demo.cu:48) and
+// the cam_z > 0 test (demo.cu:43) are known to pass and are dropped (5 fewer ALU-pipe instructions).
+__device__ __forceinline__ void voxel_classify_ptx_interior(float cam_x, float cam_y, float cam_z, const Intrinsics& K,
+                                                            const float* __restrict__ depth, int im_w,
+                                                            float trunc_margin, unsigned pend_inc, unsigned exact_bit,
+                                                            unsigned& pend, unsigned& exact) {
+  asm("{\n\t"
+      ".reg .f32 r, ua, va, tu, tv, du, dv, d, e;\n\t"
+      ".reg .s32 ix, iy, idx;\n\t"
+      ".reg .u64 addr;\n\t"
+      ".reg .pred pc, pf, pb, pe;\n\t"
+      "rcp.approx.ftz.f32 r, %4;\n\t"
+      "mul.f32 ua, r, %5;\n\t"
+      "fma.rn.f32 ua, %2, ua, %7;\n\t"
+      "mul.f32 va, r, %6;\n\t"
+      "fma.rn.f32 va, %3, va, %8;\n\t"
+      "add.f32 tu, ua, 0f4B400000;\n\t"
+      "add.f32 tv, va, 0f4B400000;\n\t"
+      "sub.f32 du, tu, 0f4B400000;\n\t"
+      "sub.f32 dv, tv, 0f4B400000;\n\t"
+      "sub.f32 du, ua, du;\n\t"
+      "sub.f32 dv, va, dv;\n\t"
+      "abs.f32 du, du;\n\t"
+      "abs.f32 dv, dv;\n\t"
+      "setp.lt.f32 pc, du, %9;\n\t"
+      "setp.lt.and.f32 pc, dv, %10, pc;\n\t"
+      "mov.b32 ix, tu;\n\t"
+      "mov.b32 iy, tv;\n\t"
+      "sub.s32 ix, ix, 0x4B400000;\n\t"
+      "sub.s32 iy, iy, 0x4B400000;\n\t"
+      "mad.lo.s32 idx, iy, %11, ix;\n\t"
+      "mad.wide.u32 addr, idx, 4, %12;\n\t"
+      "mov.f32 d, 0fFF800000;\n\t"
+      "@pc ld.global.nc.f32 d, [addr];\n\t"
+      "sub.f32 e, d, %4;\n\t"
+      "setp.ge.f32 pf, e, %13;\n\t"
+      "@pf add.u32 %0, %0, %14;\n\t"
+      "abs.f32 e, e;\n\t"
+      "setp.lt.f32 pb, e, %13;\n\t"
+      "not.pred pe, pc;\n\t"
+      "or.pred pe, pe, pb;\n\t"
+      "@pe or.b32 %1, %1, %15;\n\t"
+      "}"
+      : "+r"(pend), "+r"(exact)
+      : "f"(cam_x), "f"(cam_y), "f"(cam_z), "f"(K.fx), "f"(K.fy), "f"(K.cx), "f"(K.cy), "f"(K.lim_x), "f"(K.lim_y),
+        "r"(im_w), "l"(depth), "f"(trunc_margin), "r"(pend_inc), "r"(exact_bit));
+}
+
 // demo.cu:63-66.  (t*w + 1)/(w + 1) with t == 1 is exactly 1 (numerator and denominator are
 // the same rounded sum), so the division is skipped for untouched free-space voxels.
 __device__ __forceinline__ void voxel_update(float& t, float& w, float dist) {
@@ -242,6 +293,12 @@ struct CullAccum {
   //    8..128 px; the level whose block size covers the box is read at the <= 2 x 2 blocks it touches;
   //  * e = fl(d - cam_z) <= d_max - (cz_min - cull_z) <= -trunc * (1 + 1e-4)  =>  diff = fl(e * ray) <= -trunc
   //    because ray >= 1.
+  // True when every voxel of the hull is in front of the camera and projects >= 1.5 px inside the image.
+  __device__ __forceinline__ bool interior(const IntegrateParams& P) const {
+    return (cz_min > P.cull_z + 1e-3f) && (u_min >= 1.5f) && (u_max <= (float)P.im_w - 2.5f) && (v_min >= 1.5f) &&
+           (v_max <= (float)P.im_h - 2.5f);
+  }
+
   __device__ __forceinline__ bool occluded(const IntegrateParams& P, const float* __restrict__ mips) const {
     if (!(cz_min > P.cull_z + 1e-3f)) return false;
     const float fw = (float)P.im_w, fh = (float)P.im_h;
@@ -529,8 +586,9 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
 
   // ---- per-warp frame mask (see integrate_kernel) ----
   unsigned frame_mask = (P.n_frames >= 32) ? 0xffffffffu : ((1u << P.n_frames) - 1u);
+  unsigned interior_mask = 0u;  // frames for which the whole tile projects well inside the image
   if (!DEVPOSE && P.cull_level >= 1) {
-    bool keep = false;
+    bool keep = false, inside = false;
     const int f = threadIdx.x & 31;
     if (f < P.n_frames) {
       const FramePose& ps = P.pose[f];
@@ -553,8 +611,10 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
       keep = !acc.culled() && (y_lo < P.dim_y);
       if (keep && P.cull_level >= 2 && P.mips != nullptr && P.trunc_margin > 0.0f)
         keep = !acc.occluded(P, P.mips + (int64_t)f * P.mip_stride);
+      inside = keep && acc.interior(P);
     }
     frame_mask = __ballot_sync(0xffffffffu, keep);
+    interior_mask = __ballot_sync(0xffffffffu, inside);
   }
   if (frame_mask == 0u) return;  // warp-uniform
 
@@ -596,13 +656,19 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
 
     unsigned exact = 0u;  // bit k*VEC + j: voxel needs voxel_observation_exact
     if (active) {
-      auto plane_body = [&](int k, unsigned& pk) {
+      const bool tile_interior =
+          SANITIZED && USE_PTX && kRolled && !P.no_interior && ((interior_mask >> f) & 1u);  // warp-uniform
+      auto plane_body = [&](int k, unsigned& pk, auto interior_tag) {
+        constexpr bool kInterior = decltype(interior_tag)::value;
         const float t2 = __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), ps.tz);
         const float zx = __fmul_rn(ps.m8, t2), zy = __fmul_rn(ps.m9, t2), zz = __fmul_rn(ps.m10, t2);
         unsigned ex = 0u;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          if constexpr (SANITIZED && USE_PTX) {
+          if constexpr (SANITIZED && USE_PTX && kInterior) {
+            voxel_classify_ptx_interior(__fadd_rn(sx[j], zx), __fadd_rn(sy[j], zy), __fadd_rn(sz[j], zz), K, depth,
+                                        P.im_w, P.trunc_margin, 1u << (8 * j), 1u << j, pk, ex);
+          } else if constexpr (SANITIZED && USE_PTX) {
             voxel_classify_ptx(__fadd_rn(sx[j], zx), __fadd_rn(sy[j], zy), __fadd_rn(sz[j], zz), K, depth, P.im_w,
                                P.im_h, P.trunc_margin, 1u << (8 * j), 1u << j, pk, ex);
           } else {
@@ -617,16 +683,25 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
       };
       // block-uniform bound: only the topmost z group of a slab is ragged
       if constexpr (kRolled) {
+        if (tile_interior) {
 #pragma unroll ROLL
-        for (int k = 0; k < zcount; ++k) {
-          unsigned pk = s_pend[k][threadIdx.x];
-          plane_body(k, pk);
-          s_pend[k][threadIdx.x] = pk;
+          for (int k = 0; k < zcount; ++k) {
+            unsigned pk = s_pend[k][threadIdx.x];
+            plane_body(k, pk, std::true_type{});
+            s_pend[k][threadIdx.x] = pk;
+          }
+        } else {
+#pragma unroll ROLL
+          for (int k = 0; k < zcount; ++k) {
+            unsigned pk = s_pend[k][threadIdx.x];
+            plane_body(k, pk, std::false_type{});
+            s_pend[k][threadIdx.x] = pk;
+          }
         }
       } else {
 #pragma unroll
         for (int k = 0; k < ZT; ++k)
-          if (k < zcount) plane_body(k, pend_reg[k]);
+          if (k < zcount) plane_body(k, pend_reg[k], std::false_type{});
       }
     }
 
@@ -1063,6 +1138,9 @@ cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
     case 18: return launch_integrate_t<4, 8, false, 5, true, true, 2, true>(p, nullptr, nullptr, s);
     case 19: return launch_integrate_t<4, 8, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
     case 20: return launch_integrate_t<4, 8, false, 5, true, true, 2>(p, nullptr, nullptr, s);
+    case 21: return launch_integrate_t<4, 4, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
+    case 22: return launch_integrate_t<4, 4, false, 6, true, true, 4, true>(p, nullptr, nullptr, s);
+    case 23: return launch_integrate_t<4, 2, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
     default: return launch_integrate_t<4, 8, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
   }
 }

@@ -45,6 +45,7 @@ struct IntegrateParams {
   int mip_stride, mip_w[5], mip_off[5];
   int fast_level;        // 0: every voxel through the exact path, 1: fast classification first
   int variant;           // tuning variant of the kernel instantiation (0 = production)
+  int no_interior;       // validation: never use the interior-tile classification
   int no_ptx;            // validation: use the C++ classification instead of the PTX block
   int z_reverse;         // dispatch the z groups of the slab in descending order
   int force_lx;          // tuning: threads of a warp laid along x (0 = choose by lane waste)
