@@ -27,7 +27,8 @@ EXPORTED_SYMBOLS = [
     "tsdf_copy_surface", "tsdf_surface_device_ptr", "tsdf_write_ply", "tsdf_write_bin", "tsdf_load_matrix",
     "tsdf_read_depth_png", "tsdf_read_depth_png_u16", "tsdf_depth_from_u16", "tsdf_multiply_matrix",
     "tsdf_invert_matrix", "tsdf_Integrate", "tsdf_SaveVoxelGrid2SurfacePointCloud", "tsdf_last_error",
-    "tsdf_version", "tsdf_device_count", "tsdf_selftest_rounding",
+    "tsdf_version", "tsdf_device_count", "tsdf_selftest_rounding", "tsdf_ComputeTDF", "tsdf_tdf_grid_from_points",
+    "tsdf_point_cloud_to_tdf",
 ]
 
 
@@ -91,6 +92,9 @@ def load_library() -> C.CDLL:
                            C.c_float, C.c_float, C.c_float, vp, vp, vp],
         "tsdf_SaveVoxelGrid2SurfacePointCloud": [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                                  C.c_float, C.c_float, vp, vp, C.c_float, C.c_float],
+        "tsdf_ComputeTDF": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp],
+        "tsdf_tdf_grid_from_points": [vp, C.c_int64, C.c_float, C.c_int32, vp, vp],
+        "tsdf_point_cloud_to_tdf": [vp, C.c_int64, vp, vp, C.c_float, C.c_float, vp],
         "tsdf_device_count": [C.POINTER(C.c_int32)],
         "tsdf_selftest_rounding": [C.c_int32, i64p],
     }
@@ -209,6 +213,32 @@ def Integrate(cam_K, cam2base, depth_im, im_height, im_width, dim_x, dim_y, dim_
     _check(load_library().tsdf_Integrate(_ptr(cam_K), _ptr(cam2base), _ptr(depth_im), im_height, im_width, dim_x,
                                          dim_y, dim_z, ox, oy, oz, voxel_size, trunc_margin, _ptr(tsdf),
                                          _ptr(weight), stream), "tsdf_Integrate")
+
+
+def ComputeTDF(occ, tdf, dim_x, dim_y, dim_z, ox, oy, oz, voxel_size, trunc_margin, stream=0):
+    """core/demo.cu:22-27 argument list (without CUDA_LOOP_IDX); DEVICE pointers / CUDA tensors."""
+    _check(load_library().tsdf_ComputeTDF(_ptr(occ), _ptr(tdf), dim_x, dim_y, dim_z, ox, oy, oz, voxel_size,
+                                          trunc_margin, stream), "tsdf_ComputeTDF")
+
+
+def tdf_grid_from_points(pts, voxel_size=0.01, padding=15):
+    """core/demo.cu:100-126 -> (dims int32[3], origin float32[3])."""
+    pts = _f32(pts)
+    dims, origin = np.zeros(3, np.int32), np.zeros(3, np.float32)
+    _check(load_library().tsdf_tdf_grid_from_points(pts.ctypes.data, pts.size // 3, voxel_size, padding, dims.ctypes.data,
+                                                    origin.ctypes.data), "tsdf_tdf_grid_from_points")
+    return dims, origin
+
+
+def point_cloud_to_tdf(pts, dims, origin, voxel_size=0.01, trunc_margin=0.05) -> np.ndarray:
+    """core/demo.cu:128-163: TDF grid [dz, dy, dx] of a host point cloud (computed on the GPU)."""
+    pts = _f32(pts)
+    dims = np.ascontiguousarray(dims, np.int32)
+    origin = _f32(origin, 3)
+    out = np.empty((int(dims[2]), int(dims[1]), int(dims[0])), np.float32)
+    _check(load_library().tsdf_point_cloud_to_tdf(pts.ctypes.data, pts.size // 3, dims.ctypes.data, origin.ctypes.data,
+                                                  voxel_size, trunc_margin, out.ctypes.data), "tsdf_point_cloud_to_tdf")
+    return out
 
 
 def device_count() -> int:

@@ -624,6 +624,53 @@ int tsdf_SaveVoxelGrid2SurfacePointCloud(const char* file_name, int voxel_grid_d
   return tsdf_write_ply(file_name, pts.data(), n);
 }
 
+int tsdf_ComputeTDF(const float* voxel_grid_occ, float* voxel_grid_TDF, int voxel_grid_dim_x, int voxel_grid_dim_y,
+                    int voxel_grid_dim_z, float voxel_grid_origin_x, float voxel_grid_origin_y, float voxel_grid_origin_z,
+                    float voxel_size, float trunc_margin, void* stream) {
+  (void)voxel_grid_origin_x; (void)voxel_grid_origin_y; (void)voxel_grid_origin_z;  // unused by the reference kernel too
+  if (!voxel_grid_occ || !voxel_grid_TDF) return set_err(TSDF_ERR_ARG, "NULL device pointer");
+  if (voxel_grid_dim_x <= 0 || voxel_grid_dim_y <= 0 || voxel_grid_dim_z <= 0) return set_err(TSDF_ERR_ARG, "non-positive size");
+  const int64_t n = (int64_t)voxel_grid_dim_x * voxel_grid_dim_y * voxel_grid_dim_z;
+  if (n > INT32_MAX) return set_err(TSDF_ERR_ARG, "grid exceeds the reference's int voxel index");
+  const int radius = (int)roundf(trunc_margin / voxel_size);  // core/demo.cu:37
+  if (radius < 1 || radius > 100) return set_err(TSDF_ERR_ARG, "search radius %d out of range", radius);
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned short* scratch = nullptr;
+  CK(cudaMallocAsync(&scratch, (size_t)n * 2 * sizeof(unsigned short), s));
+  cudaError_t e = tsdf::launch_compute_tdf(voxel_grid_occ, voxel_grid_TDF, scratch, voxel_grid_dim_x, voxel_grid_dim_y,
+                                           voxel_grid_dim_z, radius, s);
+  cudaFreeAsync(scratch, s);
+  CK(e);
+  return TSDF_OK;
+}
+
+int tsdf_point_cloud_to_tdf(const float* pts, int64_t n_pts, const int32_t dims[3], const float origin[3],
+                            float voxel_size, float trunc_margin, float* tdf_host) {
+  if (!pts || !dims || !origin || !tdf_host || n_pts < 0) return set_err(TSDF_ERR_ARG, "bad argument");
+  const int64_t n = (int64_t)dims[0] * dims[1] * dims[2];
+  if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || n > INT32_MAX) return set_err(TSDF_ERR_ARG, "bad grid size");
+  float *d_pts = nullptr, *d_occ = nullptr, *d_tdf = nullptr;
+  int rc = TSDF_OK;
+  cudaError_t e = cudaMalloc(&d_pts, (size_t)(n_pts > 0 ? n_pts : 1) * 3 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_occ, (size_t)n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_tdf, (size_t)n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(d_pts, pts, (size_t)n_pts * 3 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(d_occ, 0, (size_t)n * sizeof(float));   // core/demo.cu:129-130
+  if (e == cudaSuccess) e = cudaMemset(d_tdf, 0, (size_t)n * sizeof(float));   // core/demo.cu:140-141
+  if (e == cudaSuccess)
+    e = tsdf::launch_tdf_scatter_points(d_pts, n_pts, d_occ, dims[0], dims[1], dims[2], origin[0], origin[1], origin[2],
+                                        voxel_size, 0);
+  if (e != cudaSuccess) rc = set_err(TSDF_ERR_CUDA, "tsdf_point_cloud_to_tdf: %s", cudaGetErrorString(e));
+  if (!rc) rc = tsdf_ComputeTDF(d_occ, d_tdf, dims[0], dims[1], dims[2], origin[0], origin[1], origin[2], voxel_size,
+                                trunc_margin, nullptr);
+  if (!rc) {
+    e = cudaMemcpy(tdf_host, d_tdf, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = set_err(TSDF_ERR_CUDA, "tsdf_point_cloud_to_tdf: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_pts); cudaFree(d_occ); cudaFree(d_tdf);
+  return rc;
+}
+
 int tsdf_selftest_rounding(int32_t device, int64_t* mismatches) {
   if (!mismatches) return set_err(TSDF_ERR_ARG, "mismatches is NULL");
   CK(cudaSetDevice(device));

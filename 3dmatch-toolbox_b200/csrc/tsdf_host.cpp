@@ -10,6 +10,8 @@
 
 #include <zlib.h>
 
+#include <cmath>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -105,6 +107,24 @@ void tsdf_depth_from_u16(const uint16_t* depth_mm, int64_t n, float* depth) {
     if (d > 6.0f) d = 0;
     depth[i] = d;
   }
+}
+
+// core/demo.cu:100-126: bounding box of the point cloud -> grid dimensions (with padding) and origin.
+int tsdf_tdf_grid_from_points(const float* pts, int64_t n_pts, float voxel_size, int32_t padding, int32_t dims[3],
+                              float origin[3]) {
+  if (!pts || n_pts <= 0 || !dims || !origin || !(voxel_size > 0)) return fail(TSDF_ERR_ARG, "tsdf_tdf_grid_from_points: bad argument");
+  float lo[3] = {pts[0], pts[1], pts[2]}, hi[3] = {pts[0], pts[1], pts[2]};
+  for (int64_t i = 0; i < n_pts; ++i)
+    for (int a = 0; a < 3; ++a) {
+      const float p = pts[3 * i + a];
+      if (p < lo[a]) lo[a] = p;
+      if (p > hi[a]) hi[a] = p;
+    }
+  for (int a = 0; a < 3; ++a) {
+    dims[a] = (int32_t)(roundf((hi[a] - lo[a]) / voxel_size) + 1 + padding * 2);   // :119-121
+    origin[a] = lo[a] - padding * voxel_size + voxel_size / 2;                      // :123-125
+  }
+  return TSDF_OK;
 }
 
 // utils.hpp:26-33 (header, exactly 7 lines: core/demo.cu:76-86 parses it by line count) and

@@ -15,6 +15,9 @@
  *   depth-fusion/utils.hpp:74-86   ReadDepth                       -> tsdf_read_depth_png, tsdf_depth_from_u16
  *   depth-fusion/utils.hpp:89-109  multiply_matrix                 -> tsdf_multiply_matrix
  *   depth-fusion/utils.hpp:112-238 invert_matrix                   -> tsdf_invert_matrix
+ *   depth-fusion/fuseSceneFragments.m:36-81 fragment loop          -> bin/fuse_fragments (built on this ABI)
+ *   core/demo.cu:22-57,100-163     ComputeTDF + grid/occupancy     -> tsdf_ComputeTDF, tsdf_tdf_grid_from_points,
+ *                                                                     tsdf_point_cloud_to_tdf   
  *
  * Conventions: plain pointers and sizes only; every entry point returns an int status
  * (TSDF_OK == 0) unless stated; the library never prints and never calls exit();
@@ -144,6 +147,23 @@ int tsdf_SaveVoxelGrid2SurfacePointCloud(const char *file_name, int voxel_grid_d
                                          float voxel_grid_origin_y, float voxel_grid_origin_z,
                                          const float *voxel_grid_TSDF, const float *voxel_grid_weight,
                                          float tsdf_thresh, float weight_thresh);
+
+/* ---- TSDF consumer: truncated distance function of a point cloud (core/demo.cu) ------------------ */
+/* Replaces the launch loop `for CUDA_LOOP_IDX: ComputeTDF<<<2880, 512>>>(CUDA_LOOP_IDX, ...)`
+ * (core/demo.cu:22-27, :153-160): one call covers the whole grid.  Device pointers owned by the caller;
+ * voxel_grid_TDF is read-modify-write exactly like the kernel (zero it first, core/demo.cu:140-141).
+ * Bit-identical to the reference kernel, via a separable exact distance transform instead of the
+ * (2R+1)^3 brute-force window. */
+int tsdf_ComputeTDF(const float *voxel_grid_occ, float *voxel_grid_TDF, int voxel_grid_dim_x, int voxel_grid_dim_y,
+                    int voxel_grid_dim_z, float voxel_grid_origin_x, float voxel_grid_origin_y,
+                    float voxel_grid_origin_z, float voxel_size, float trunc_margin, void *stream);
+/* core/demo.cu:100-126 (host): grid dimensions and origin from the cloud's bounding box + padding voxels. */
+int tsdf_tdf_grid_from_points(const float *pts, int64_t n_pts, float voxel_size, int32_t padding, int32_t dims[3],
+                              float origin[3]);
+/* core/demo.cu:128-163: occupancy scatter + TDF of a HOST point cloud; tdf_host receives
+ * dims[0]*dims[1]*dims[2] floats (x fastest), writable as tdf.bin with tsdf_write_bin. */
+int tsdf_point_cloud_to_tdf(const float *pts, int64_t n_pts, const int32_t dims[3], const float origin[3],
+                            float voxel_size, float trunc_margin, float *tdf_host);
 
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 const char *tsdf_last_error(void);

@@ -144,6 +144,58 @@ def load_matrix(path, count):
     return got, out
 
 
+def compute_tdf(occ, dims, voxel_size=0.01, trunc_margin=0.05, tdf=None):
+    """core/demo.cu:22-57 brute force; occ shaped [dz, dy, dx]; returns tdf of the same shape."""
+    dx, dy, dz = (int(v) for v in dims)
+    occ = _f32(occ, dx * dy * dz)
+    tdf = np.zeros(dx * dy * dz, np.float32) if tdf is None else _f32(tdf, dx * dy * dz).copy()
+    lib().oracle_compute_tdf(_p(occ), _p(tdf), C.c_int(dx), C.c_int(dy), C.c_int(dz), C.c_float(voxel_size),
+                             C.c_float(trunc_margin))
+    return tdf.reshape(dz, dy, dx)
+
+
+def tdf_grid_from_points(pts, voxel_size=0.01, padding=15, want_occ=True):
+    pts = _f32(pts)
+    dims, origin = np.zeros(3, np.int32), np.zeros(3, np.float32)
+    lib().oracle_tdf_grid_from_points(_p(pts), C.c_int64(pts.size // 3), C.c_float(voxel_size), C.c_int(padding), _p(dims),
+                                      _p(origin), None)
+    occ = None
+    if want_occ:
+        occ = np.zeros(int(dims[0]) * int(dims[1]) * int(dims[2]), np.float32)
+        lib().oracle_tdf_grid_from_points(_p(pts), C.c_int64(pts.size // 3), C.c_float(voxel_size), C.c_int(padding),
+                                          _p(dims), _p(origin), _p(occ))
+        occ = occ.reshape(int(dims[2]), int(dims[1]), int(dims[0]))
+    return dims, origin, occ
+
+
+REF_TDF_HOST_LIB = HERE / "_ref" / "libref_tdf_host.so"
+REF_TDF_CUDA_LIB = HERE / "_ref" / "libref_tdf_cuda.so"
+
+
+def ref_host_compute_tdf(occ, dims, voxel_size=0.01, trunc_margin=0.05):
+    """The reference's ComputeTDF kernel body (core/demo.cu:22-57) on host threads."""
+    dx, dy, dz = (int(v) for v in dims)
+    occ = _f32(occ, dx * dy * dz).copy()
+    tdf = np.zeros(dx * dy * dz, np.float32)
+    _load(REF_TDF_HOST_LIB).ref_host_compute_tdf(_p(occ), _p(tdf), C.c_int(dx), C.c_int(dy), C.c_int(dz), C.c_float(0),
+                                                 C.c_float(0), C.c_float(0), C.c_float(voxel_size), C.c_float(trunc_margin))
+    return tdf.reshape(dz, dy, dx)
+
+
+def ref_cuda_compute_tdf(occ, dims, voxel_size=0.01, trunc_margin=0.05):
+    """The reference's ComputeTDF kernel compiled for sm_100a, launched <<<2880, 512>>> per loop. (tdf, ms)."""
+    dx, dy, dz = (int(v) for v in dims)
+    occ = _f32(occ, dx * dy * dz)
+    tdf = np.zeros(dx * dy * dz, np.float32)
+    ms = C.c_float(0)
+    rc = _load(REF_TDF_CUDA_LIB).ref_cuda_compute_tdf(_p(occ), _p(tdf), C.c_int(dx), C.c_int(dy), C.c_int(dz), C.c_float(0),
+                                                      C.c_float(0), C.c_float(0), C.c_float(voxel_size),
+                                                      C.c_float(trunc_margin), C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"reference ComputeTDF failed: cudaError {rc}")
+    return tdf.reshape(dz, dy, dx), ms.value
+
+
 # ---- the reference's own code on host threads (oracle/_ref/libref_host.so) --------------------------
 
 def ref_host():

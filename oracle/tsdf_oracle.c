@@ -290,6 +290,70 @@ int oracle_load_matrix(const char *path, int count, float *out)
     return got;
 }
 
+/* core/demo.cu:22-57.  One "thread" per voxel index; the index -> (x, y, z) decomposition is done in float
+ * exactly as the kernel does (:33-35), which mis-addresses voxels once the index exceeds 2^24. */
+void oracle_compute_tdf(const float *occ, float *tdf, int dim_x, int dim_y, int dim_z,
+                        float voxel_size, float trunc_margin)
+{
+    const int64_t total = (int64_t)dim_x * dim_y * dim_z;
+    /* core/demo.cu:37: (int)round(trunc_margin / voxel_size); nvcc resolves round(float) to roundf */
+    const int radius = (int)roundf(trunc_margin / voxel_size);
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t idx = 0; idx < total; ++idx) {
+        int v = (int)idx;
+        int pz = (int)floorf((float)v / ((float)dim_x * (float)dim_y));
+        int py = (int)floorf(((float)v - ((float)pz * (float)dim_x * (float)dim_y)) / (float)dim_x);
+        int px = (int)((float)v - ((float)pz * (float)dim_x * (float)dim_y) - ((float)py * (float)dim_x));
+        if (occ[idx] > 0) {                                   /* :39-42 */
+            tdf[idx] = 1.0f;
+            continue;
+        }
+        int x0 = px - radius > 0 ? px - radius : 0, x1 = px + radius + 1 < dim_x ? px + radius + 1 : dim_x;
+        int y0 = py - radius > 0 ? py - radius : 0, y1 = py + radius + 1 < dim_y ? py + radius + 1 : dim_y;
+        int z0 = pz - radius > 0 ? pz - radius : 0, z1 = pz + radius + 1 < dim_z ? pz + radius + 1 : dim_z;
+        for (int ix = x0; ix < x1; ++ix)                      /* :45-56 */
+            for (int iy = y0; iy < y1; ++iy)
+                for (int iz = z0; iz < z1; ++iz) {
+                    int64_t n = (int64_t)iz * dim_x * dim_y + (int64_t)iy * dim_x + ix;
+                    if (occ[n] > 0) {
+                        float xd = (float)(px - ix), yd = (float)(py - iy), zd = (float)(pz - iz);
+                        float dist = sqrtf(xd * xd + yd * yd + zd * zd) / (float)radius;
+                        if ((1.0f - dist) > tdf[idx])
+                            tdf[idx] = 1.0f - dist;
+                    }
+                }
+    }
+}
+
+static float minf_(float a, float b) { return a < b ? a : b; }
+static float maxf_(float a, float b) { return a > b ? a : b; }
+
+/* core/demo.cu:100-136 */
+void oracle_tdf_grid_from_points(const float *pts, int64_t n_pts, float voxel_size, int padding,
+                                 int dims[3], float origin[3], float *occ)
+{
+    float lo[3] = {pts[0], pts[1], pts[2]}, hi[3] = {pts[0], pts[1], pts[2]};
+    for (int64_t i = 0; i < n_pts; ++i)
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = minf_(lo[a], pts[3 * i + a]);
+            hi[a] = maxf_(hi[a], pts[3 * i + a]);
+        }
+    for (int a = 0; a < 3; ++a) {
+        /* :119-121 -- round() of a float expression (C++ picks the float overload) + ints */
+        dims[a] = (int)(roundf((hi[a] - lo[a]) / voxel_size) + 1 + padding * 2);
+        /* :123-125 */
+        origin[a] = lo[a] - padding * voxel_size + voxel_size / 2;
+    }
+    if (!occ)
+        return;
+    for (int64_t i = 0; i < n_pts; ++i) {                     /* :131-136 */
+        int gx = (int)roundf((pts[3 * i + 0] - origin[0]) / voxel_size);
+        int gy = (int)roundf((pts[3 * i + 1] - origin[1]) / voxel_size);
+        int gz = (int)roundf((pts[3 * i + 2] - origin[2]) / voxel_size);
+        occ[(int64_t)gz * dims[1] * dims[0] + (int64_t)gy * dims[0] + gx] = 1.0f;
+    }
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

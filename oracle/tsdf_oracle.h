@@ -73,6 +73,17 @@ int oracle_write_tsdf_bin(const char *path, int64_t dim_x, int64_t dim_y, int64_
 /* utils.hpp:60-70: M*N whitespace-separated floats, row-major.  Returns values read. */
 int oracle_load_matrix(const char *path, int count, float *out);
 
+/* core/demo.cu:22-57 -- ComputeTDF over the whole grid (all CUDA_LOOP_IDX passes), brute force, including the
+ * reference's float index decomposition (core/demo.cu:33-35).  tdf is read-modify-write like the kernel
+ * (the caller zero-initialises it, core/demo.cu:140-141). */
+void oracle_compute_tdf(const float *occ, float *tdf, int dim_x, int dim_y, int dim_z,
+                        float voxel_size, float trunc_margin);
+
+/* core/demo.cu:100-136 -- grid placement and occupancy from a point cloud.  dims/origin are outputs;
+ * occ (dims[0]*dims[1]*dims[2] floats, zero-initialised by the caller) may be NULL to query the size only. */
+void oracle_tdf_grid_from_points(const float *pts, int64_t n_pts, float voxel_size, int padding,
+                                 int dims[3], float origin[3], float *occ);
+
 int oracle_num_threads(void);
 
 #ifdef __cplusplus
