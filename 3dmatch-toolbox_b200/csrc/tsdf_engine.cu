@@ -126,6 +126,7 @@ void fill_params(const tsdf_volume* v, tsdf::IntegrateParams* p) {
   p->force_lx = (v->tuning >> 12) & 0xff;
   p->no_ptx = (v->tuning >> 20) & 1;
   p->no_interior = (v->tuning >> 21) & 1;
+  p->no_packed = (v->tuning >> 22) & 1;
 }
 
 void pose_from_cam2base(const float* c, tsdf::FramePose* o) {

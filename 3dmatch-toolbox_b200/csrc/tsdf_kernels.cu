@@ -232,6 +232,207 @@ __device__ __forceinline__ void voxel_classify_ptx_interior(float cam_x, float c
         "r"(im_w), "l"(depth), "f"(trunc_margin), "r"(pend_inc), "r"(exact_bit));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed classification (sm_100a FFMA2 / FADD2): the same classification as voxel_classify_ptx for TWO
+// x-adjacent voxels at once.  Blackwell issues fp32 add/mul/fma on register pairs as one instruction
+// (add/mul/fma.rn.f32x2), with scalar operands broadcast for free, so the projection costs half the
+// issue slots -- the kernel is issue bound, not FMA-pipe bound.  Arithmetic per lane is identical to the
+// scalar block where exactness matters (cam_z and e = d - cam_z are single IEEE adds); the pixel
+// coordinate only has to stay inside pixel_round_margin(), which any contraction ptxas applies to the
+// f32x2 multiply-adds can only tighten.  Two further instruction savings:
+//   * the gather index is formed in floating point: fma(rint(v'), W, u' + M) = M + iy*W + ix exactly
+//     (M = 1.5 * 2^23, the sum stays below 2^24), so its bit pattern is 0x4B400000 + iy*W + ix and one
+//     mad.wide with a pre-biased base pointer gives the address;
+//   * bounds (non-interior tiles) are tested on the rounded float coordinate: |rint(u') - (W-1)/2| <=
+//     (W-1)/2, exact for integers below 2^22 and false for NaN / huge values.
+// sx2/sy2/sz2 hold (M0*t0 + M4*t1) of the two voxels, zx/zy/zz the plane's M8*t2 products.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ void voxel_classify_pair(f32x2_t sx2, f32x2_t sy2, f32x2_t sz2, float zx, float zy, float zz,
+                                                    const Intrinsics& K, float im_w_f, float half_w, float half_h,
+                                                    const void* depth_biased, float trunc_margin, unsigned pend_inc0,
+                                                    unsigned pend_inc1, unsigned exact_bit0, unsigned exact_bit1,
+                                                    unsigned& pend, unsigned& exact) {
+  if constexpr (INTERIOR) {
+    asm("{\n\t"
+        ".reg .b64 bz, cxx, cyy, czz, rr, kk, ua, va, tu, tv, ru, rv, du, dv, fi, dd, ee, bm, bk;\n\t"
+        ".reg .f32 z0, z1, r0, r1, a0, a1, b0, b1, i0, i1, d0, d1, e0, e1, mg;\n\t"
+        ".reg .b32 n0, n1;\n\t"
+        ".reg .u64 ad0, ad1;\n\t"
+        ".reg .pred pc0, pc1, pf0, pf1, pb0, pb1;\n\t"
+        "mov.b64 bz, {%5, %5};\n\t"
+        "add.rn.f32x2 cxx, %2, bz;\n\t"
+        "mov.b64 bz, {%6, %6};\n\t"
+        "add.rn.f32x2 cyy, %3, bz;\n\t"
+        "mov.b64 bz, {%7, %7};\n\t"
+        "add.rn.f32x2 czz, %4, bz;\n\t"
+        "mov.b64 {z0, z1}, czz;\n\t"
+        "rcp.approx.ftz.f32 r0, z0;\n\t"
+        "rcp.approx.ftz.f32 r1, z1;\n\t"
+        "mov.b64 rr, {r0, r1};\n\t"
+        "mov.b64 bk, {%8, %8};\n\t"
+        "mul.rn.f32x2 kk, rr, bk;\n\t"
+        "mov.b64 bk, {%10, %10};\n\t"
+        "fma.rn.f32x2 ua, cxx, kk, bk;\n\t"
+        "mov.b64 bk, {%9, %9};\n\t"
+        "mul.rn.f32x2 kk, rr, bk;\n\t"
+        "mov.b64 bk, {%11, %11};\n\t"
+        "fma.rn.f32x2 va, cyy, kk, bk;\n\t"
+        "mov.f32 mg, 0f4B400000;\n\t"
+        "mov.b64 bm, {mg, mg};\n\t"
+        "add.rn.f32x2 tu, ua, bm;\n\t"
+        "add.rn.f32x2 tv, va, bm;\n\t"
+        "sub.rn.f32x2 ru, tu, bm;\n\t"
+        "sub.rn.f32x2 rv, tv, bm;\n\t"
+        "sub.rn.f32x2 du, ua, ru;\n\t"
+        "sub.rn.f32x2 dv, va, rv;\n\t"
+        "mov.b64 bk, {%14, %14};\n\t"
+        "fma.rn.f32x2 fi, rv, bk, tu;\n\t"
+        "mov.b64 {a0, a1}, du;\n\t"
+        "mov.b64 {b0, b1}, dv;\n\t"
+        "abs.f32 a0, a0;\n\t"
+        "abs.f32 a1, a1;\n\t"
+        "abs.f32 b0, b0;\n\t"
+        "abs.f32 b1, b1;\n\t"
+        "setp.lt.f32 pc0, a0, %12;\n\t"
+        "setp.lt.f32 pc1, a1, %12;\n\t"
+        "setp.lt.and.f32 pc0, b0, %13, pc0;\n\t"
+        "setp.lt.and.f32 pc1, b1, %13, pc1;\n\t"
+        "mov.b64 {i0, i1}, fi;\n\t"
+        "mov.b32 n0, i0;\n\t"
+        "mov.b32 n1, i1;\n\t"
+        "mad.wide.u32 ad0, n0, 4, %15;\n\t"
+        "mad.wide.u32 ad1, n1, 4, %15;\n\t"
+        "ld.global.nc.f32 d0, [ad0];\n\t"
+        "ld.global.nc.f32 d1, [ad1];\n\t"
+        "mov.b64 dd, {d0, d1};\n\t"
+        "sub.rn.f32x2 ee, dd, czz;\n\t"
+        "mov.b64 {e0, e1}, ee;\n\t"
+        "setp.ge.and.f32 pf0, e0, %16, pc0;\n\t"   // the gather is unconditional here: an uncertain pixel
+        "setp.ge.and.f32 pf1, e1, %16, pc1;\n\t"   // must not count (the exact path will)
+        "@pf0 add.u32 %0, %0, %17;\n\t"
+        "@pf1 add.u32 %0, %0, %18;\n\t"
+        "abs.f32 e0, e0;\n\t"
+        "abs.f32 e1, e1;\n\t"
+        "setp.lt.f32 pb0, e0, %16;\n\t"
+        "setp.lt.f32 pb1, e1, %16;\n\t"
+        "not.pred pc0, pc0;\n\t"
+        "not.pred pc1, pc1;\n\t"
+        "or.pred pb0, pb0, pc0;\n\t"
+        "or.pred pb1, pb1, pc1;\n\t"
+        "@pb0 or.b32 %1, %1, %19;\n\t"
+        "@pb1 or.b32 %1, %1, %20;\n\t"
+        "}"
+        : "+r"(pend), "+r"(exact)
+        : "l"(sx2), "l"(sy2), "l"(sz2), "f"(zx), "f"(zy), "f"(zz), "f"(K.fx), "f"(K.fy), "f"(K.cx), "f"(K.cy),
+          "f"(K.lim_x), "f"(K.lim_y), "f"(im_w_f), "l"(depth_biased), "f"(trunc_margin), "r"(pend_inc0),
+          "r"(pend_inc1), "r"(exact_bit0), "r"(exact_bit1));
+  } else {
+    asm("{\n\t"
+        ".reg .b64 bz, cxx, cyy, czz, rr, kk, ua, va, tu, tv, ru, rv, du, dv, fi, dd, ee, bm, bk, qu, qv;\n\t"
+        ".reg .f32 z0, z1, r0, r1, a0, a1, b0, b1, i0, i1, d0, d1, e0, e1, mg, g0, g1, h0, h1;\n\t"
+        ".reg .b32 n0, n1;\n\t"
+        ".reg .u64 ad0, ad1;\n\t"
+        ".reg .pred pc0, pc1, pg0, pg1, pp0, pp1, pf0, pf1, pb0, pb1;\n\t"
+        "mov.b64 bz, {%5, %5};\n\t"
+        "add.rn.f32x2 cxx, %2, bz;\n\t"
+        "mov.b64 bz, {%6, %6};\n\t"
+        "add.rn.f32x2 cyy, %3, bz;\n\t"
+        "mov.b64 bz, {%7, %7};\n\t"
+        "add.rn.f32x2 czz, %4, bz;\n\t"
+        "mov.b64 {z0, z1}, czz;\n\t"
+        "rcp.approx.ftz.f32 r0, z0;\n\t"
+        "rcp.approx.ftz.f32 r1, z1;\n\t"
+        "mov.b64 rr, {r0, r1};\n\t"
+        "mov.b64 bk, {%8, %8};\n\t"
+        "mul.rn.f32x2 kk, rr, bk;\n\t"
+        "mov.b64 bk, {%10, %10};\n\t"
+        "fma.rn.f32x2 ua, cxx, kk, bk;\n\t"
+        "mov.b64 bk, {%9, %9};\n\t"
+        "mul.rn.f32x2 kk, rr, bk;\n\t"
+        "mov.b64 bk, {%11, %11};\n\t"
+        "fma.rn.f32x2 va, cyy, kk, bk;\n\t"
+        "mov.f32 mg, 0f4B400000;\n\t"
+        "mov.b64 bm, {mg, mg};\n\t"
+        "add.rn.f32x2 tu, ua, bm;\n\t"
+        "add.rn.f32x2 tv, va, bm;\n\t"
+        "sub.rn.f32x2 ru, tu, bm;\n\t"
+        "sub.rn.f32x2 rv, tv, bm;\n\t"
+        "sub.rn.f32x2 du, ua, ru;\n\t"
+        "sub.rn.f32x2 dv, va, rv;\n\t"
+        "mov.b64 bk, {%14, %14};\n\t"
+        "fma.rn.f32x2 fi, rv, bk, tu;\n\t"
+        "mov.b64 bk, {%21, %21};\n\t"
+        "sub.rn.f32x2 qu, ru, bk;\n\t"
+        "mov.b64 bk, {%22, %22};\n\t"
+        "sub.rn.f32x2 qv, rv, bk;\n\t"
+        "mov.b64 {a0, a1}, du;\n\t"
+        "mov.b64 {b0, b1}, dv;\n\t"
+        "mov.b64 {g0, g1}, qu;\n\t"
+        "mov.b64 {h0, h1}, qv;\n\t"
+        "abs.f32 a0, a0;\n\t"
+        "abs.f32 a1, a1;\n\t"
+        "abs.f32 b0, b0;\n\t"
+        "abs.f32 b1, b1;\n\t"
+        "abs.f32 g0, g0;\n\t"
+        "abs.f32 g1, g1;\n\t"
+        "abs.f32 h0, h0;\n\t"
+        "abs.f32 h1, h1;\n\t"
+        "setp.lt.f32 pc0, a0, %12;\n\t"
+        "setp.lt.f32 pc1, a1, %12;\n\t"
+        "setp.lt.and.f32 pc0, b0, %13, pc0;\n\t"
+        "setp.lt.and.f32 pc1, b1, %13, pc1;\n\t"
+        "setp.gt.f32 pp0, z0, 0f00000000;\n\t"
+        "setp.gt.f32 pp1, z1, 0f00000000;\n\t"
+        "setp.le.and.f32 pg0, g0, %21, pc0;\n\t"
+        "setp.le.and.f32 pg1, g1, %21, pc1;\n\t"
+        "setp.le.and.f32 pg0, h0, %22, pg0;\n\t"
+        "setp.le.and.f32 pg1, h1, %22, pg1;\n\t"
+        "and.pred pg0, pg0, pp0;\n\t"
+        "and.pred pg1, pg1, pp1;\n\t"
+        "mov.b64 {i0, i1}, fi;\n\t"
+        "mov.b32 n0, i0;\n\t"
+        "mov.b32 n1, i1;\n\t"
+        "mad.wide.u32 ad0, n0, 4, %15;\n\t"
+        "mad.wide.u32 ad1, n1, 4, %15;\n\t"
+        "mov.f32 d0, 0fFF800000;\n\t"
+        "mov.f32 d1, 0fFF800000;\n\t"
+        "@pg0 ld.global.nc.f32 d0, [ad0];\n\t"
+        "@pg1 ld.global.nc.f32 d1, [ad1];\n\t"
+        "mov.b64 dd, {d0, d1};\n\t"
+        "sub.rn.f32x2 ee, dd, czz;\n\t"
+        "mov.b64 {e0, e1}, ee;\n\t"
+        "setp.ge.f32 pf0, e0, %16;\n\t"
+        "setp.ge.f32 pf1, e1, %16;\n\t"
+        "@pf0 add.u32 %0, %0, %17;\n\t"
+        "@pf1 add.u32 %0, %0, %18;\n\t"
+        "abs.f32 e0, e0;\n\t"
+        "abs.f32 e1, e1;\n\t"
+        "setp.lt.f32 pb0, e0, %16;\n\t"
+        "setp.lt.f32 pb1, e1, %16;\n\t"
+        "not.pred pc0, pc0;\n\t"
+        "not.pred pc1, pc1;\n\t"
+        "or.pred pb0, pb0, pc0;\n\t"
+        "or.pred pb1, pb1, pc1;\n\t"
+        "and.pred pb0, pb0, pp0;\n\t"
+        "and.pred pb1, pb1, pp1;\n\t"
+        "@pb0 or.b32 %1, %1, %19;\n\t"
+        "@pb1 or.b32 %1, %1, %20;\n\t"
+        "}"
+        : "+r"(pend), "+r"(exact)
+        : "l"(sx2), "l"(sy2), "l"(sz2), "f"(zx), "f"(zy), "f"(zz), "f"(K.fx), "f"(K.fy), "f"(K.cx), "f"(K.cy),
+          "f"(K.lim_x), "f"(K.lim_y), "f"(im_w_f), "l"(depth_biased), "f"(trunc_margin), "r"(pend_inc0),
+          "r"(pend_inc1), "r"(exact_bit0), "r"(exact_bit1), "f"(half_w), "f"(half_h));
+  }
+}
+
 // demo.cu:63-66.  (t*w + 1)/(w + 1) with t == 1 is exactly 1 (numerator and denominator are
 // the same rounded sum), so the division is skipped for untouched free-space voxels.
 __device__ __forceinline__ void voxel_update(float& t, float& w, float dist) {
@@ -552,12 +753,15 @@ __device__ __forceinline__ void apply_pending(float& t, float& w, unsigned c) {
 
 constexpr int kExactQueueCap = 256;  // exact-evaluation queue entries per warp
 
-template <int VEC, int ZT, bool DEVPOSE, int MINB, bool SANITIZED, bool USE_PTX, int ROLL, bool QUEUE>
+template <int VEC, int ZT, bool DEVPOSE, int MINB, bool SANITIZED, int PTX_LEVEL, int ROLL, bool QUEUE>
 __global__ void __launch_bounds__(kBlockThreads, MINB)
 integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float* __restrict__ d_cam_K,
                          const float* __restrict__ d_cam2base) {
   static_assert(VEC == 4 || VEC == 1, "VEC");
   static_assert(VEC * ZT <= 32, "one bit of the exact mask per voxel of the patch");
+  // PTX_LEVEL: 0 = C++ classification, 1 = scalar PTX block, 2 = packed (f32x2) PTX block for voxel pairs
+  constexpr bool USE_PTX = PTX_LEVEL >= 1;
+  constexpr bool kPacked = SANITIZED && PTX_LEVEL >= 2 && VEC == 4 && ROLL > 0;
   const int lx_mask = (1 << P.lx_shift) - 1;
   const int lx = threadIdx.x & lx_mask;
   const int ly = threadIdx.x >> P.lx_shift;
@@ -582,6 +786,20 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
   } else {
     K.fx = P.fx; K.fy = P.fy; K.cx = P.cx; K.cy = P.cy;
     K.lim_x = P.lim_x; K.lim_y = P.lim_y;
+  }
+
+  // ---- packed variant: the plane products M8*t2 (demo.cu:32,37,39-41) of every (frame, plane) of this block,
+  //      formed once per block with the reference's operations and broadcast from shared memory in the loop
+  __shared__ float4 s_ztab[kPacked ? kMaxBatch * ZT : 1];
+  if constexpr (kPacked) {
+    const int nf = DEVPOSE ? 1 : P.n_frames;
+    for (int e = threadIdx.x; e < nf * ZT; e += kBlockThreads) {
+      const int f = e / ZT, k = e - f * ZT;
+      const FramePose& ps = DEVPOSE ? dev_pose : P.pose[f];
+      const float t2 = __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), ps.tz);
+      s_ztab[e] = make_float4(__fmul_rn(ps.m8, t2), __fmul_rn(ps.m9, t2), __fmul_rn(ps.m10, t2), 0.0f);
+    }
+    __syncthreads();
   }
 
   // ---- per-warp frame mask (see integrate_kernel) ----
@@ -658,8 +876,31 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
     if (active) {
       const bool tile_interior =
           SANITIZED && USE_PTX && kRolled && !P.no_interior && ((interior_mask >> f) & 1u);  // warp-uniform
+      // packed variant: the voxel pairs (0,1) and (2,3) as f32x2 operands; gather base biased by the bit
+      // pattern of the rint magic (see voxel_classify_pair)
+      f32x2_t sx2[2], sy2[2], sz2[2];
+      const char* depth_biased = reinterpret_cast<const char*>(depth) - 4ll * (long long)kRintMagicBits;
+      const float im_w_f = (float)P.im_w, half_w = 0.5f * (float)(P.im_w - 1), half_h = 0.5f * (float)(P.im_h - 1);
+      if constexpr (kPacked) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          sx2[h] = pack2(sx[2 * h], sx[2 * h + 1]);
+          sy2[h] = pack2(sy[2 * h], sy[2 * h + 1]);
+          sz2[h] = pack2(sz[2 * h], sz[2 * h + 1]);
+        }
+      }
       auto plane_body = [&](int k, unsigned& pk, auto interior_tag) {
         constexpr bool kInterior = decltype(interior_tag)::value;
+        if constexpr (kPacked) {
+          const float4 zt = s_ztab[(DEVPOSE ? 0 : f) * ZT + k];
+          unsigned ex = 0u;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            voxel_classify_pair<kInterior>(sx2[h], sy2[h], sz2[h], zt.x, zt.y, zt.z, K, im_w_f, half_w, half_h,
+                                           depth_biased, P.trunc_margin, 1u << (16 * h), 1u << (16 * h + 8),
+                                           1u << (2 * h), 1u << (2 * h + 1), pk, ex);
+          exact |= ex << (k * VEC);
+        } else {
         const float t2 = __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), ps.tz);
         const float zx = __fmul_rn(ps.m8, t2), zy = __fmul_rn(ps.m9, t2), zz = __fmul_rn(ps.m10, t2);
         unsigned ex = 0u;
@@ -680,6 +921,7 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
           }
         }
         exact |= ex << (k * VEC);
+        }
       };
       // block-uniform bound: only the topmost z group of a slab is ragged
       if constexpr (kRolled) {
@@ -1101,12 +1343,16 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
   if (FAST && (p.fast_level == 0 || !(p.trunc_margin > 0.0f)))
     return launch_integrate_t<VEC, ZT, DEVPOSE, MINB, false, false, 0, false>(p, d_K, d_pose, s);
   if constexpr (PENDING) {
-    if (p.sanitized && !p.no_ptx)
-      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, true, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+    // the packed classification needs |M + iy*W + ix| < 2^24 for its floating-point gather index
+    const bool can_pack = (int64_t)p.im_w * p.im_h < (1 << 22) && VEC == 4 && ROLL > 0;
+    if (p.sanitized && !p.no_ptx && !p.no_packed && can_pack)
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, 2, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+    else if (p.sanitized && !p.no_ptx)
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, 1, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
     else if (p.sanitized)
-      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, false, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, 0, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
     else
-      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, false, false, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+      integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, false, 0, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
   }
   else
     integrate_kernel<VEC, ZT, DEVPOSE, MINB, FAST><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
@@ -1141,6 +1387,9 @@ cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
     case 21: return launch_integrate_t<4, 4, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
     case 22: return launch_integrate_t<4, 4, false, 6, true, true, 4, true>(p, nullptr, nullptr, s);
     case 23: return launch_integrate_t<4, 2, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
+    case 24: return launch_integrate_t<4, 8, false, 4, true, true, 2, true>(p, nullptr, nullptr, s);
+    case 25: return launch_integrate_t<4, 8, false, 5, true, true, 4, true>(p, nullptr, nullptr, s);
+    case 26: return launch_integrate_t<4, 8, false, 5, true, true, 1, true>(p, nullptr, nullptr, s);
     default: return launch_integrate_t<4, 8, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
   }
 }

@@ -47,6 +47,7 @@ struct IntegrateParams {
   int variant;           // tuning variant of the kernel instantiation (0 = production)
   int no_interior;       // validation: never use the interior-tile classification
   int no_ptx;            // validation: use the C++ classification instead of the PTX block
+  int no_packed;         // validation: scalar PTX block instead of the packed (f32x2) pair block
   int z_reverse;         // dispatch the z groups of the slab in descending order
   int force_lx;          // tuning: threads of a warp laid along x (0 = choose by lane waste)
   int sanitized;         // depth frames went through sanitize_depth_kernel (invalid = -inf)
