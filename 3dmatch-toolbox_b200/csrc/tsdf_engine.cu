@@ -63,6 +63,8 @@ struct tsdf_volume {
   int n_sub = 1;
   cudaStream_t sub_stream[kMaxSub] = {};
   int64_t sub_z[kMaxSub + 1] = {};  // sub-slab i = local planes [sub_z[i], sub_z[i+1])
+  uint2* tile_masks[kMaxSub] = {};  // per sub-slab scratch of the frame-mask pre-pass (tile_mask_kernel)
+  int64_t tile_mask_cap[kMaxSub] = {};
   int last_slot = -1;
   int64_t ring_pos = 0;
   // surface extraction
@@ -174,9 +176,18 @@ int launch_chunk(tsdf_volume* v, int slot, const float* cam2base, int n) {
     q.z_begin = (int)(v->d.z_begin + v->sub_z[i]);
     cudaStream_t st = (v->n_sub == 1) ? v->stream : v->sub_stream[i];
     if (v->n_sub > 1) CK(cudaStreamWaitEvent(st, v->ev_ready[slot], 0));
+    if (v->cull >= 1 && !(v->tuning & (1 << 23))) {
+      // scratch for the frame-mask pre-pass; passes of one sub-slab are ordered on its stream, so one buffer each
+      if (!v->tile_masks[i]) {
+        v->tile_mask_cap[i] = tsdf::tile_mask_entries(q.dim_x, q.dim_y, q.nz);
+        CK(cudaMalloc(&v->tile_masks[i], (size_t)v->tile_mask_cap[i] * sizeof(uint2)));
+      }
+      q.tile_masks = v->tile_masks[i];
+      q.tile_mask_cap = v->tile_mask_cap[i];
+    }
     CK(tsdf::launch_integrate(q, st));
     CK(cudaEventRecord(v->ev_join[slot][i], st));
-    v->stats.kernel_launches += 1;
+    v->stats.kernel_launches += tsdf::last_integrate_launches();
   }
   v->slot_busy[slot] = true;
   v->last_slot = slot;
@@ -384,6 +395,7 @@ void tsdf_destroy(tsdf_volume* v) {
     for (int i = 0; i < kMaxSub; ++i)
       if (v->ev_join[s][i]) cudaEventDestroy(v->ev_join[s][i]);
   }
+  for (int i = 0; i < kMaxSub; ++i) cudaFree(v->tile_masks[i]);
   if (v->owns_volume) { cudaFree(v->tsdf); cudaFree(v->weight); }
   cudaFree(v->tile_offsets);
   cudaFree(v->xyz);

@@ -751,9 +751,68 @@ __device__ __forceinline__ void apply_pending(float& t, float& w, unsigned c) {
   }
 }
 
-constexpr int kExactQueueCap = 256;  // exact-evaluation queue entries per warp
+// Frame-vs-tile test of the K-frame kernels: can frame f touch any voxel of the warp tile whose lowest corner is
+// (x_lo, y_lo, z_lo) [global indices], and does the whole tile project well inside the image?  Frustum: five
+// half-space tests on the 8 corners; occlusion: hierarchical-Z against the frame's depth max-pyramid.
+template <int VEC, int ZT>
+__device__ __forceinline__ void tile_frame_test(const IntegrateParams& P, const Intrinsics& K, int f, int x_lo, int y_lo,
+                                                int rows_per_warp, int z_lo, bool& keep, bool& inside) {
+  const FramePose& ps = P.pose[f];
+  const int x_hi = min(P.dim_x - 1, x_lo + ((VEC << P.lx_shift) - 1));
+  const int y_hi = min(P.dim_y - 1, y_lo + rows_per_warp - 1);
+  const int z_hi = z_lo + ZT - 1;
+  CullAccum acc;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float bx = fmaf((float)((c & 1) ? x_hi : x_lo), P.voxel_size, P.ox) - ps.tx;
+    const float by = fmaf((float)((c & 2) ? y_hi : y_lo), P.voxel_size, P.oy) - ps.ty;
+    const float bz = fmaf((float)((c & 4) ? z_hi : z_lo), P.voxel_size, P.oz) - ps.tz;
+    acc.add(fmaf(ps.m0, bx, fmaf(ps.m4, by, ps.m8 * bz)), fmaf(ps.m1, bx, fmaf(ps.m5, by, ps.m9 * bz)),
+            fmaf(ps.m2, bx, fmaf(ps.m6, by, ps.m10 * bz)), P, K);
+  }
+  keep = !acc.culled() && (y_lo < P.dim_y);
+  if (keep && P.cull_level >= 2 && P.mips != nullptr && P.trunc_margin > 0.0f)
+    keep = !acc.occluded(P, P.mips + (int64_t)f * P.mip_stride);
+  inside = keep && acc.interior(P);
+}
 
-template <int VEC, int ZT, bool DEVPOSE, int MINB, bool SANITIZED, int PTX_LEVEL, int ROLL, bool QUEUE>
+// Pre-pass of a K-frame launch: the frame masks of every warp tile of the slab, one thread per (tile, frame).
+// Inside the fusion kernel this test is a long dependent chain executed by half-empty warps while their block's
+// other warps wait; here it runs at full occupancy over all tiles at once (~0.3 % of the fusion kernel's
+// instructions) and the fusion warps start with one 8-byte load.  out[tile] = {frame mask, interior mask},
+// tile = (z group * n_yt + y tile) * n_xt + x tile, the numbering integrate_pending_kernel derives from its block
+// and warp indices.
+template <int VEC, int ZT>
+__global__ void __launch_bounds__(256)
+tile_mask_kernel(const __grid_constant__ IntegrateParams P, int n_xt, int n_yt, int64_t n_tiles, int nf_shift) {
+  Intrinsics K;
+  K.fx = P.fx; K.fy = P.fy; K.cx = P.cx; K.cy = P.cy; K.lim_x = P.lim_x; K.lim_y = P.lim_y;
+  const unsigned lane = threadIdx.x & 31u;
+  const int f = (int)(lane & ((1u << nf_shift) - 1u));
+  const unsigned sub = lane >> nf_shift;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t tile = warp * (32 >> nf_shift) + sub;
+  bool keep = false, inside = false;
+  if (tile < n_tiles && f < P.n_frames) {
+    const int xt = (int)(tile % n_xt);
+    const int64_t r = tile / n_xt;
+    const int yt = (int)(r % n_yt), zg = (int)(r / n_yt);
+    const int rows_per_warp = 32 >> P.lx_shift;
+    tile_frame_test<VEC, ZT>(P, K, f, (xt << P.lx_shift) * VEC, yt * rows_per_warp, rows_per_warp, P.z_begin + zg * ZT, keep,
+                             inside);
+  }
+  const unsigned bk = __ballot_sync(0xffffffffu, keep), bi = __ballot_sync(0xffffffffu, inside);
+  if (f == 0 && tile < n_tiles) {
+    const unsigned sel = (nf_shift == 5) ? 0xffffffffu : ((1u << (1u << nf_shift)) - 1u);
+    P.tile_masks[tile] = make_uint2((bk >> (sub << nf_shift)) & sel, (bi >> (sub << nf_shift)) & sel);
+  }
+}
+
+constexpr int kExactQueueCap = 256;  // exact-evaluation queue entries per warp
+constexpr int kDeferredQueueCap = 128;  // deferred (multi-frame) queue entries per warp
+constexpr int kBlockQueueCap = 2048;    // block-shared queue entries (QUEUE == 3)
+
+template <int VEC, int ZT, bool DEVPOSE, int MINB, bool SANITIZED, int PTX_LEVEL, int ROLL, int QUEUE, bool PREMASK = false>
 __global__ void __launch_bounds__(kBlockThreads, MINB)
 integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float* __restrict__ d_cam_K,
                          const float* __restrict__ d_cam2base) {
@@ -802,39 +861,47 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
     __syncthreads();
   }
 
-  // ---- per-warp frame mask (see integrate_kernel) ----
+  // ---- per-warp frame mask (see integrate_kernel): read from the pre-pass (tile_mask_kernel) when the launcher
+  //      ran it, else computed here with lane f testing frame f ----
   unsigned frame_mask = (P.n_frames >= 32) ? 0xffffffffu : ((1u << P.n_frames) - 1u);
   unsigned interior_mask = 0u;  // frames for which the whole tile projects well inside the image
   if (!DEVPOSE && P.cull_level >= 1) {
-    bool keep = false, inside = false;
-    const int f = threadIdx.x & 31;
-    if (f < P.n_frames) {
-      const FramePose& ps = P.pose[f];
-      const int rows_per_warp = 32 >> P.lx_shift;
-      const int x_lo = (blockIdx.x << P.lx_shift) * VEC;
-      const int x_hi = min(P.dim_x - 1, x_lo + ((VEC << P.lx_shift) - 1));
-      const int y_lo = blockIdx.y * rows_per_block + (threadIdx.x >> 5) * rows_per_warp;
-      const int y_hi = min(P.dim_y - 1, y_lo + rows_per_warp - 1);
-      const int z_lo = P.z_begin + zl0;
-      const int z_hi = z_lo + ZT - 1;
-      CullAccum acc;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float bx = fmaf((float)((c & 1) ? x_hi : x_lo), P.voxel_size, P.ox) - ps.tx;
-        const float by = fmaf((float)((c & 2) ? y_hi : y_lo), P.voxel_size, P.oy) - ps.ty;
-        const float bz = fmaf((float)((c & 4) ? z_hi : z_lo), P.voxel_size, P.oz) - ps.tz;
-        acc.add(fmaf(ps.m0, bx, fmaf(ps.m4, by, ps.m8 * bz)), fmaf(ps.m1, bx, fmaf(ps.m5, by, ps.m9 * bz)),
-                fmaf(ps.m2, bx, fmaf(ps.m6, by, ps.m10 * bz)), P, K);
+    const int rows_per_warp = 32 >> P.lx_shift;
+    if constexpr (PREMASK) {
+      const int64_t tile = ((int64_t)(zl0 / ZT) * (gridDim.y * (kBlockThreads / 32)) +
+                            (blockIdx.y * (kBlockThreads / 32) + (threadIdx.x >> 5))) * gridDim.x + blockIdx.x;
+      const uint2 m = __ldg(P.tile_masks + tile);
+      frame_mask = m.x;
+      interior_mask = m.y;
+    } else {
+      bool keep = false, inside = false;
+      const int f = threadIdx.x & 31;
+      if (f < P.n_frames) {
+        const int x_lo = (blockIdx.x << P.lx_shift) * VEC;
+        const int y_lo = blockIdx.y * rows_per_block + (threadIdx.x >> 5) * rows_per_warp;
+        tile_frame_test<VEC, ZT>(P, K, f, x_lo, y_lo, rows_per_warp, P.z_begin + zl0, keep, inside);
       }
-      keep = !acc.culled() && (y_lo < P.dim_y);
-      if (keep && P.cull_level >= 2 && P.mips != nullptr && P.trunc_margin > 0.0f)
-        keep = !acc.occluded(P, P.mips + (int64_t)f * P.mip_stride);
-      inside = keep && acc.interior(P);
+      frame_mask = __ballot_sync(0xffffffffu, keep);
+      interior_mask = __ballot_sync(0xffffffffu, inside);
     }
-    frame_mask = __ballot_sync(0xffffffffu, keep);
-    interior_mask = __ballot_sync(0xffffffffu, inside);
   }
-  if (frame_mask == 0u) return;  // warp-uniform
+  // QUEUE == 3: the exact-evaluation queue is shared by the block, so its 8 warps walk the UNION of their frame
+  // masks in lockstep (two barriers per frame); a warp whose own mask lacks the frame only helps with the queue
+  constexpr bool kBlockQ = QUEUE == 3 && ROLL > 0;
+  __shared__ unsigned s_bmask;
+  __shared__ unsigned s_bq_count[2], s_bq_valid[2];
+  __shared__ unsigned short s_bq[kBlockQ ? kBlockQueueCap : 1];
+  unsigned loop_mask = frame_mask;
+  if constexpr (kBlockQ) {
+    if (threadIdx.x == 0) { s_bmask = 0u; s_bq_count[0] = s_bq_count[1] = 0u; s_bq_valid[0] = s_bq_valid[1] = 0u; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && frame_mask != 0u) atomicOr(&s_bmask, frame_mask);
+    __syncthreads();
+    loop_mask = s_bmask;
+    if (loop_mask == 0u) return;  // block-uniform
+  } else {
+    if (frame_mask == 0u) return;  // warp-uniform
+  }
 
   const float base_y = __fadd_rn(P.oy, __fmul_rn((float)y, P.voxel_size));  // demo.cu:31
   const int64_t plane = (int64_t)P.dim_y * P.dim_x;
@@ -845,7 +912,69 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
   // times and the hot loop fits the instruction cache.
   constexpr bool kRolled = ROLL > 0;
   __shared__ unsigned s_pend[kRolled ? ZT : 1][kRolled ? kBlockThreads : 1];
-  __shared__ unsigned short s_queue[(QUEUE && kRolled) ? kBlockThreads / 32 : 1][(QUEUE && kRolled) ? kExactQueueCap : 1];
+  __shared__ unsigned short s_queue[(QUEUE == 1 && kRolled) ? kBlockThreads / 32 : 1][(QUEUE == 1 && kRolled) ? kExactQueueCap : 1];
+  // QUEUE == 2: deferred queue.  An entry is (owner lane, voxel slot, frame, snapshot of the voxel's pending count);
+  // entries of several frames are evaluated together, 32 at a time, so the lanes are full (see drain_deferred)
+  constexpr bool kDeferred = QUEUE == 2 && kRolled;
+  __shared__ unsigned s_dq[kDeferred ? kBlockThreads / 32 : 1][kDeferred ? kDeferredQueueCap : 1];
+  unsigned dq_count = 0u;  // warp-uniform
+  // Evaluates and applies every queued entry.  Evaluation (voxel_observation_exact) does not depend on the voxel's
+  // state, so the 32 entries of a round are computed in parallel whatever their frames; the APPLICATION is ordered:
+  // entries were appended in frame order, entries of one voxel that share a round are applied in lane (= queue)
+  // order (match.any groups, one sub-step per rank), rounds follow each other.  Every entry first flushes the
+  // pending free-space count snapshot taken when it was queued -- the observations older than the entry -- so each
+  // voxel still sees all its updates in ascending frame order (demo.cu:63-66).
+  auto drain_deferred = [&]() {
+    if constexpr (kDeferred) {
+      const unsigned lane = threadIdx.x & 31u;
+      const unsigned* q = s_dq[threadIdx.x >> 5];
+      __syncwarp();
+      for (unsigned base = 0; base < dq_count; base += 32u) {
+        const unsigned i = base + lane;
+        const bool valid = i < dq_count;
+        float dj = kNoObservation;
+        unsigned c = 0u, key = 0x80000000u | lane;  // invalid lanes: unique keys
+        int64_t idx = 0;
+        if (valid) {
+          const unsigned item = q[i];
+          key = item & 0x3ffu;
+          c = (item >> 16) & 0xffu;
+          const int fr = DEVPOSE ? 0 : (int)((item >> 10) & 31u);
+          const int owner_t = (int)((threadIdx.x & ~31u) | (item & 31u));
+          const int s = (int)((item >> 5) & 31u), j = s & (VEC - 1), k = s / VEC;
+          const int o_xu = (blockIdx.x << P.lx_shift) + (owner_t & lx_mask);
+          const int o_y = blockIdx.y * rows_per_block + (owner_t >> P.lx_shift);
+          FramePose pq;
+          if (DEVPOSE) pq = dev_pose; else pq = P.pose[fr];
+          // the owner's arithmetic, operation for operation (demo.cu:30-41)
+          const float q0 = __fsub_rn(__fadd_rn(P.ox, __fmul_rn((float)(o_xu * VEC + j), P.voxel_size)), pq.tx);
+          const float q1 = __fsub_rn(__fadd_rn(P.oy, __fmul_rn((float)o_y, P.voxel_size)), pq.ty);
+          const float q2 = __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), pq.tz);
+          const float cam_x = __fadd_rn(__fadd_rn(__fmul_rn(pq.m0, q0), __fmul_rn(pq.m4, q1)), __fmul_rn(pq.m8, q2));
+          const float cam_y = __fadd_rn(__fadd_rn(__fmul_rn(pq.m1, q0), __fmul_rn(pq.m5, q1)), __fmul_rn(pq.m9, q2));
+          const float cam_z = __fadd_rn(__fadd_rn(__fmul_rn(pq.m2, q0), __fmul_rn(pq.m6, q1)), __fmul_rn(pq.m10, q2));
+          dj = voxel_observation_exact<true>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy,
+                                             P.depth + (int64_t)fr * P.frame_stride, P.im_w, P.im_h, P.trunc_margin);
+          idx = ((int64_t)(zl0 + k) * P.dim_y + o_y) * (int64_t)P.dim_x + (int64_t)o_xu * VEC + j;
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const unsigned rank = __popc(grp & ((1u << lane) - 1u));
+        const bool work = valid && (dj != kNoObservation || c != 0u);
+        for (unsigned r = 0; __any_sync(0xffffffffu, work && rank >= r); ++r) {
+          if (work && rank == r) {
+            float t = P.tsdf[idx], w = P.weight[idx];
+            apply_pending(t, w, c);
+            if (dj != kNoObservation) voxel_update(t, w, dj);
+            P.tsdf[idx] = t;
+            P.weight[idx] = w;
+          }
+          __syncwarp();
+        }
+      }
+      dq_count = 0u;
+      __syncwarp();
+    }
+  };
   unsigned pend_reg[kRolled ? 1 : ZT];
   if constexpr (kRolled) {
 #pragma unroll
@@ -855,10 +984,12 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
     for (int k = 0; k < ZT; ++k) pend_reg[k] = 0u;
   }
 
-  for (unsigned fm = frame_mask; fm != 0u; fm &= fm - 1u) {
+  unsigned bq_parity = 0u;
+  for (unsigned fm = loop_mask; fm != 0u; fm &= fm - 1u) {
     const int f = __ffs(fm) - 1;
     const FramePose& ps = DEVPOSE ? dev_pose : P.pose[f];
     const float* __restrict__ depth = P.depth + (int64_t)f * P.frame_stride;
+    const bool warp_sees_frame = !kBlockQ || ((frame_mask >> f) & 1u);  // warp-uniform
 
     // demo.cu:30-41: (M0*t0 + M4*t1) per x, M8*t2 per z
     const float t1 = __fsub_rn(base_y, ps.ty);
@@ -873,7 +1004,7 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
     }
 
     unsigned exact = 0u;  // bit k*VEC + j: voxel needs voxel_observation_exact
-    if (active) {
+    if (active && warp_sees_frame) {
       const bool tile_interior =
           SANITIZED && USE_PTX && kRolled && !P.no_interior && ((interior_mask >> f) & 1u);  // warp-uniform
       // packed variant: the voxel pairs (0,1) and (2,3) as f32x2 operands; gather base biased by the bit
@@ -952,7 +1083,92 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
     //      so they are queued in shared memory and handed out one per lane; results go back to the owner's
     //      pending counts through shared-memory atomics, in-band ones are applied by the lane that computed
     //      them.  Frame order per voxel is kept: the queue is drained before the next frame starts.
-    if constexpr (QUEUE && kRolled) {
+    if constexpr (kDeferred) {
+      const unsigned lane = threadIdx.x & 31u;
+      const unsigned n_mine = __popc(exact);
+      const unsigned total = __reduce_add_sync(0xffffffffu, n_mine);
+      if (total != 0u) {  // warp-uniform
+        if (dq_count + total > (unsigned)kDeferredQueueCap) drain_deferred();
+        if (total <= (unsigned)kDeferredQueueCap) {
+          unsigned incl = n_mine;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += v;
+          }
+          unsigned* q = s_dq[threadIdx.x >> 5];
+          unsigned pos = dq_count + incl - n_mine;
+          while (exact != 0u) {
+            const unsigned s = (unsigned)(__ffs(exact) - 1);
+            exact &= exact - 1u;
+            const unsigned sh = 8u * (s & (unsigned)(VEC - 1));
+            // snapshot the voxel's pending count into the entry and restart it: free-space observations counted
+            // from here on are younger than this entry
+            unsigned* pw = &s_pend[s / VEC][threadIdx.x];
+            const unsigned pk = *pw;
+            *pw = pk & ~(0xffu << sh);
+            q[pos++] = lane | (s << 5) | ((unsigned)f << 10) | (((pk >> sh) & 0xffu) << 16);
+          }
+          dq_count += total;
+        }
+        // (a frame with more exact voxels than the queue holds falls through to the per-lane loop below, after
+        //  the drain above has applied everything older)
+      }
+    }
+    if constexpr (kBlockQ) {
+      // push: a lane reserves room for all its exact voxels with one shared-memory atomic (order inside a frame is
+      // irrelevant: the entries of a frame are distinct voxels); lanes that do not fit keep `exact` and fall through
+      // to the per-lane loop below
+      const unsigned n_mine = __popc(exact);
+      if (n_mine != 0u) {
+        unsigned pos = atomicAdd(&s_bq_count[bq_parity], n_mine);
+        if (pos + n_mine <= (unsigned)kBlockQueueCap) {
+          atomicMax(&s_bq_valid[bq_parity], pos + n_mine);
+          while (exact != 0u) {
+            const unsigned s = (unsigned)(__ffs(exact) - 1);
+            exact &= exact - 1u;
+            s_bq[pos++] = (unsigned short)(threadIdx.x | (s << 8));
+          }
+        }
+      }
+      __syncthreads();
+      const unsigned total = s_bq_valid[bq_parity];
+      if (threadIdx.x == 0) { s_bq_count[bq_parity ^ 1u] = 0u; s_bq_valid[bq_parity ^ 1u] = 0u; }  // next frame's
+      for (unsigned i = threadIdx.x; i < total; i += kBlockThreads) {
+        const unsigned item = s_bq[i];
+        const int owner_t = (int)(item & 0xffu);
+        const int s = (int)(item >> 8), j = s & (VEC - 1), k = s / VEC;
+        const int o_xu = (blockIdx.x << P.lx_shift) + (owner_t & lx_mask);
+        const int o_y = blockIdx.y * rows_per_block + (owner_t >> P.lx_shift);
+        // the owner's arithmetic, operation for operation (demo.cu:30-41)
+        const float q0 = __fsub_rn(__fadd_rn(P.ox, __fmul_rn((float)(o_xu * VEC + j), P.voxel_size)), ps.tx);
+        const float q1 = __fsub_rn(__fadd_rn(P.oy, __fmul_rn((float)o_y, P.voxel_size)), ps.ty);
+        const float q2 = __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), ps.tz);
+        const float cam_x = __fadd_rn(__fadd_rn(__fmul_rn(ps.m0, q0), __fmul_rn(ps.m4, q1)), __fmul_rn(ps.m8, q2));
+        const float cam_y = __fadd_rn(__fadd_rn(__fmul_rn(ps.m1, q0), __fmul_rn(ps.m5, q1)), __fmul_rn(ps.m9, q2));
+        const float cam_z = __fadd_rn(__fadd_rn(__fmul_rn(ps.m2, q0), __fmul_rn(ps.m6, q1)), __fmul_rn(ps.m10, q2));
+        const float dj = voxel_observation_exact<true>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy, depth, P.im_w,
+                                                       P.im_h, P.trunc_margin);
+        if (dj != kNoObservation) {
+          unsigned* pw = &s_pend[k][owner_t];
+          if (dj == 1.0f) {
+            atomicAdd(pw, 1u << (8 * j));
+          } else {
+            const unsigned old = atomicAnd(pw, ~(0xffu << (8 * j)));
+            const int64_t idx = ((int64_t)(zl0 + k) * P.dim_y + o_y) * (int64_t)P.dim_x + (int64_t)o_xu * VEC + j;
+            float t = P.tsdf[idx], w = P.weight[idx];
+            apply_pending(t, w, (old >> (8 * j)) & 0xffu);
+            const float w_new = __fadd_rn(w, 1.0f);
+            t = __fdiv_rn(__fadd_rn(__fmul_rn(t, w), dj), w_new);
+            P.tsdf[idx] = t;
+            P.weight[idx] = w_new;
+          }
+        }
+      }
+      __syncthreads();  // every result is in s_pend / global memory before the next frame's classification
+      bq_parity ^= 1u;
+    }
+    if constexpr (QUEUE == 1 && kRolled) {
       const unsigned lane = threadIdx.x & 31u;
       const unsigned n_mine = __popc(exact);
       unsigned incl = n_mine;
@@ -1064,6 +1280,8 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
       }
     }
   }
+
+  drain_deferred();
 
   // ---- write-back of the pending free-space counts: coalesced, warp-uniform per plane ----
   auto write_back = [&](int k, unsigned pk) {
@@ -1312,6 +1530,8 @@ __global__ void __launch_bounds__(256) selftest_rounding_kernel(unsigned long lo
   if (bad) atomicAdd(mismatches, bad);
 }
 
+thread_local int g_integrate_launches = 0;  // kernels the last launch_integrate*() call enqueued
+
 int ilog2(int v) {
   int s = 0;
   while ((1 << (s + 1)) <= v) ++s;
@@ -1319,7 +1539,7 @@ int ilog2(int v) {
 }
 
 template <int VEC, int ZT, bool DEVPOSE, int MINB, bool FAST = true, bool PENDING = false, int ROLL = 0,
-          bool QUEUE = false>
+          int QUEUE = 0>
 cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float* d_pose, cudaStream_t s) {
   p.nx_units = p.dim_x / VEC;
   p.lim_x = 0.5f - pixel_round_margin((float)p.im_w, p.cx);
@@ -1340,12 +1560,32 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
   dim3 grid((unsigned)((p.nx_units + best_lx - 1) / best_lx), (unsigned)((p.dim_y + rows - 1) / rows),
             (unsigned)((p.nz + ZT - 1) / ZT));
   if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
+  g_integrate_launches = 1;
   if (FAST && (p.fast_level == 0 || !(p.trunc_margin > 0.0f)))
     return launch_integrate_t<VEC, ZT, DEVPOSE, MINB, false, false, 0, false>(p, d_K, d_pose, s);
   if constexpr (PENDING) {
     // the packed classification needs |M + iy*W + ix| < 2^24 for its floating-point gather index
     const bool can_pack = (int64_t)p.im_w * p.im_h < (1 << 22) && VEC == 4 && ROLL > 0;
-    if (p.sanitized && !p.no_ptx && !p.no_packed && can_pack)
+    const bool packed = p.sanitized && !p.no_ptx && !p.no_packed && can_pack;
+    // frame-mask pre-pass into the engine's scratch buffer (production kernel only; otherwise the kernel computes
+    // its masks itself)
+    bool premask = false;
+    if constexpr (!DEVPOSE) {
+      const int64_t n_xt = grid.x, n_yt = (int64_t)grid.y * (kBlockThreads / 32), n_tiles = n_xt * n_yt * grid.z;
+      if (packed && p.tile_masks != nullptr && p.cull_level >= 1 && n_tiles <= p.tile_mask_cap) {
+        int nf_shift = 0;
+        while ((1 << nf_shift) < p.n_frames) ++nf_shift;
+        const int64_t threads = ((n_tiles + (32 >> nf_shift) - 1) / (32 >> nf_shift)) * 32;
+        tile_mask_kernel<VEC, ZT><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p, (int)n_xt, (int)n_yt, n_tiles, nf_shift);
+        ++g_integrate_launches;
+        premask = true;
+      }
+    }
+    if (!premask) p.tile_masks = nullptr;
+    if (packed && premask) {
+      if constexpr (!DEVPOSE)
+        integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, 2, ROLL, QUEUE, true><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
+    } else if (packed)
       integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, 2, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
     else if (p.sanitized && !p.no_ptx)
       integrate_pending_kernel<VEC, ZT, DEVPOSE, MINB, true, 1, ROLL, QUEUE><<<grid, kBlockThreads, 0, s>>>(p, d_K, d_pose);
@@ -1361,9 +1601,11 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
 
 }  // namespace
 
+int last_integrate_launches() { return g_integrate_launches; }
+
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
   if (p.n_frames < 1 || p.n_frames > kMaxBatch) return cudaErrorInvalidValue;
-  if (p.dim_x % 4 != 0) return launch_integrate_t<1, 8, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
+  if (p.dim_x % 4 != 0) return launch_integrate_t<1, 8, false, 6, true, true, 2, 3>(p, nullptr, nullptr, s);
   switch (p.variant) {  // tuning variants (tsdf_volume_desc.reserved0); 0 is the production choice
     case 1: return launch_integrate_t<4, 4, false, 2>(p, nullptr, nullptr, s);
     case 2: return launch_integrate_t<4, 4, false, 3>(p, nullptr, nullptr, s);
@@ -1390,7 +1632,12 @@ cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
     case 24: return launch_integrate_t<4, 8, false, 4, true, true, 2, true>(p, nullptr, nullptr, s);
     case 25: return launch_integrate_t<4, 8, false, 5, true, true, 4, true>(p, nullptr, nullptr, s);
     case 26: return launch_integrate_t<4, 8, false, 5, true, true, 1, true>(p, nullptr, nullptr, s);
-    default: return launch_integrate_t<4, 8, false, 6, true, true, 2, true>(p, nullptr, nullptr, s);
+    case 27: return launch_integrate_t<4, 8, false, 6, true, true, 2, 2>(p, nullptr, nullptr, s);
+    case 28: return launch_integrate_t<4, 8, false, 5, true, true, 2, 2>(p, nullptr, nullptr, s);
+    case 29: return launch_integrate_t<4, 8, false, 6, true, true, 2, 3>(p, nullptr, nullptr, s);
+    case 30: return launch_integrate_t<4, 8, false, 5, true, true, 2, 3>(p, nullptr, nullptr, s);
+    case 31: return launch_integrate_t<4, 8, false, 6, true, true, 2, 1>(p, nullptr, nullptr, s);  // per-warp queue
+    default: return launch_integrate_t<4, 8, false, 6, true, true, 2, 3>(p, nullptr, nullptr, s);
   }
 }
 
@@ -1404,6 +1651,22 @@ cudaError_t launch_integrate_devpose(IntegrateParams p, const float* d_cam_K, co
                     ((reinterpret_cast<uintptr_t>(p.weight) & 15u) == 0);
   if (vec4) return launch_integrate_t<4, 8, true, 6, true, true, 2, true>(p, d_cam_K, d_cam2base, s);
   return launch_integrate_t<1, 8, true, 6, true, true, 2, true>(p, d_cam_K, d_cam2base, s);
+}
+
+int64_t tile_mask_entries(int dim_x, int dim_y, int64_t nz) {
+  // production shape: VEC = 4 (or 1), ZT = 8, lx in {8, 16, 32} threads along x, 8 warps of 32 / lx rows per block
+  const int64_t zg = (nz + 7) / 8;
+  int64_t worst = 0;
+  for (int vec = 1; vec <= 4; vec += 3) {
+    if (vec == 4 && dim_x % 4 != 0) continue;
+    const int64_t nxu = dim_x / vec;
+    for (int lx = 4; lx <= 32; lx <<= 1) {
+      const int64_t xt = (nxu + lx - 1) / lx, rows = kBlockThreads / lx;
+      const int64_t yt = ((dim_y + rows - 1) / rows) * (kBlockThreads / 32);
+      if (xt * yt * zg > worst) worst = xt * yt * zg;
+    }
+  }
+  return worst;
 }
 
 cudaError_t launch_fill(float* tsdf, float* weight, int64_t n, cudaStream_t s) {

@@ -80,10 +80,11 @@ def test_fast_classification_equals_exact_path(pkg, sequence):
     for dims, voxel in [((320, 320, 320), 0.0096), ((512, 256, 128), 0.006)]:
         trunc = float(np.float32(voxel) * np.float32(5))
         exact = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=8, cull_level=0, tuning=256)
-        for tuning in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 1 << 21, 1 << 22,
-                       (1 << 22) | (1 << 21), (1 << 22) | 18, 1 << 20, (1 << 20) | 7, (1 << 20) | 13):
+        for tuning in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 1 << 21, 1 << 22,
+                       (1 << 22) | (1 << 21), (1 << 22) | 18, 1 << 23, (1 << 23) | 27, 1 << 20, (1 << 20) | 7, (1 << 20) | 13):
             # bit 20: C++ classification instead of PTX, bit 21: no interior-tile variant, bit 22: scalar PTX block
-            # instead of the packed (f32x2) pair block
+            # instead of the packed (f32x2) pair block, bit 23: frame masks inside the kernel instead of the pre-pass;
+            # variants 27/28: deferred multi-frame exact queue
             fast = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=8, cull_level=2, tuning=tuning)
             for a, b, name in zip(fast, exact, ("tsdf", "weight", "points")):
                 assert_bit_equal(a, b, f"{name} variant {tuning} dims {dims}")
