@@ -15,7 +15,7 @@
 //   --image W H              depth image size (reference: 640 480, demo.cu:87-88)
 //   --bin [path]             also write the TSDF volume as tsdf.bin (demo.cu:196-213)
 //   --ply path               surface point cloud path (default tsdf.ply)
-//   --batch K                frames fused per pass over the volume (default 16)
+//   --batch K                frames fused per pass over the volume (default 8)
 //   --device N               CUDA device ordinal (default 0)
 //   --thresh T W             surface thresholds (reference: 0.2 1.0, demo.cu:194)
 //
@@ -68,7 +68,7 @@ int main(int argc, char* argv[]) {
   long long dim_x = 500, dim_y = 500, dim_z = 500;
   // extensions
   std::string ply_path = "tsdf.ply", bin_path;
-  int batch = 16, device = 0;
+  int batch = 8, device = 0;
   float tsdf_thresh = 0.2f, weight_thresh = 1.0f;  // demo.cu:194
 
   int next = 1;

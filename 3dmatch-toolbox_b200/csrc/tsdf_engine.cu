@@ -326,7 +326,7 @@ int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
   v->n_vox = v->nz * d.dim_y * d.dim_x;
   v->frame_px = (int64_t)d.im_width * d.im_height;
   v->mip = tsdf::make_mip_layout(d.im_width, d.im_height);
-  v->batch = d.max_batch ? d.max_batch : 16;
+  v->batch = d.max_batch ? d.max_batch : 8;   // measured optimum on B200 (K = 4..32 swept, profiles/README.md)
   v->cull = (d.cull_level < 0 || d.cull_level > 2) ? 2 : d.cull_level;
   v->tuning = d.reserved0;
   {
@@ -360,7 +360,9 @@ int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
   {
     // sub-slabs: cut at multiples of 8 planes (the z extent of a thread's voxel patch)
     int want = (v->tuning >> 10) & 3;
-    if (want == 0) want = 2;
+    if (v->tuning & (1 << 24)) want = 4;
+    if (want == 0) want = 3;   // measured on 1/8 slabs of the 1024^3 grid: 1 stream +38 %, 2 +25 %, 3 +19 % over the
+                               // cost of the same planes inside one big launch
     if (v->nz < 64) want = 1;
     v->n_sub = want;
     for (int i = 0; i <= want; ++i) v->sub_z[i] = (i == want) ? v->nz : ((v->nz * i / want) / 8) * 8;

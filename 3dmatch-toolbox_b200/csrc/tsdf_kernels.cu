@@ -850,16 +850,21 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
   // ---- packed variant: the plane products M8*t2 (demo.cu:32,37,39-41) of every (frame, plane) of this block,
   //      formed once per block with the reference's operations and broadcast from shared memory in the loop
   __shared__ float4 s_ztab[kPacked ? kMaxBatch * ZT : 1];
-  if constexpr (kPacked) {
-    const int nf = DEVPOSE ? 1 : P.n_frames;
-    for (int e = threadIdx.x; e < nf * ZT; e += kBlockThreads) {
-      const int f = e / ZT, k = e - f * ZT;
-      const FramePose& ps = DEVPOSE ? dev_pose : P.pose[f];
-      const float t2 = __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), ps.tz);
-      s_ztab[e] = make_float4(__fmul_rn(ps.m8, t2), __fmul_rn(ps.m9, t2), __fmul_rn(ps.m10, t2), 0.0f);
+  constexpr bool kBlockQ = QUEUE == 3 && ROLL > 0;
+  auto fill_ztab = [&](unsigned frames) {
+    if constexpr (kPacked) {
+      const int nf = DEVPOSE ? 1 : P.n_frames;
+      for (int e = threadIdx.x; e < nf * ZT; e += kBlockThreads) {
+        const int f = e / ZT, k = e - f * ZT;
+        if (!((frames >> f) & 1u)) continue;
+        const FramePose& ps = DEVPOSE ? dev_pose : P.pose[f];
+        const float t2 = __fsub_rn(__fadd_rn(P.oz, __fmul_rn((float)(P.z_begin + zl0 + k), P.voxel_size)), ps.tz);
+        s_ztab[e] = make_float4(__fmul_rn(ps.m8, t2), __fmul_rn(ps.m9, t2), __fmul_rn(ps.m10, t2), 0.0f);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
+  };
+  if constexpr (!kBlockQ) fill_ztab(0xffffffffu);  // (before any warp of the block may leave)
 
   // ---- per-warp frame mask (see integrate_kernel): read from the pre-pass (tile_mask_kernel) when the launcher
   //      ran it, else computed here with lane f testing frame f ----
@@ -887,18 +892,19 @@ integrate_pending_kernel(const __grid_constant__ IntegrateParams P, const float*
   }
   // QUEUE == 3: the exact-evaluation queue is shared by the block, so its 8 warps walk the UNION of their frame
   // masks in lockstep (two barriers per frame); a warp whose own mask lacks the frame only helps with the queue
-  constexpr bool kBlockQ = QUEUE == 3 && ROLL > 0;
-  __shared__ unsigned s_bmask;
+  __shared__ unsigned s_wmask[kBlockThreads / 32];
   __shared__ unsigned s_bq_count[2], s_bq_valid[2];
   __shared__ unsigned short s_bq[kBlockQ ? kBlockQueueCap : 1];
   unsigned loop_mask = frame_mask;
   if constexpr (kBlockQ) {
-    if (threadIdx.x == 0) { s_bmask = 0u; s_bq_count[0] = s_bq_count[1] = 0u; s_bq_valid[0] = s_bq_valid[1] = 0u; }
+    if ((threadIdx.x & 31) == 0) s_wmask[threadIdx.x >> 5] = frame_mask;
+    if (threadIdx.x == 0) { s_bq_count[0] = s_bq_count[1] = 0u; s_bq_valid[0] = s_bq_valid[1] = 0u; }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0 && frame_mask != 0u) atomicOr(&s_bmask, frame_mask);
-    __syncthreads();
-    loop_mask = s_bmask;
-    if (loop_mask == 0u) return;  // block-uniform
+    loop_mask = 0u;
+#pragma unroll
+    for (int w = 0; w < kBlockThreads / 32; ++w) loop_mask |= s_wmask[w];
+    if (loop_mask == 0u) return;  // block-uniform: no frame reaches this block
+    fill_ztab(loop_mask);
   } else {
     if (frame_mask == 0u) return;  // warp-uniform
   }

@@ -109,14 +109,14 @@ def measure_plane_cost(volume_factory, depth, poses, dim_z, chunk=64, sample_bat
     return np.maximum(np.interp(np.arange(dim_z), centers, density), 1e-9)
 
 
-def refine_plane_cost(plane_cost, ranges, rank_ms) -> np.ndarray:
+def refine_plane_cost(plane_cost, ranges, rank_ms, damping: float = 1.0) -> np.ndarray:
     """One step of feedback balancing: scale the per-plane cost model by measured / modelled time of
     every slab (interpolated between slab centres), so that the next equal-cost partition evens out
     the measured rank times.  `rank_ms[r]` is the time rank r needed for slab `ranges[r]`."""
     cost = np.asarray(plane_cost, dtype=np.float64)
     model = np.array([cost[a:b].sum() for a, b in ranges])
     ratio = np.asarray(rank_ms, dtype=np.float64) / np.maximum(model, 1e-12)
-    ratio = ratio / ratio.mean()
+    ratio = (ratio / ratio.mean()) ** damping   # damping < 1: smaller steps, no overshoot on noisy rank times
     centers = np.array([0.5 * (a + b - 1) for a, b in ranges])
     return cost * np.interp(np.arange(len(cost)), centers, ratio)
 

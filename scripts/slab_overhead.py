@@ -32,7 +32,8 @@ def time_slab(z0, z1, batch, tuning=0):
         return vol.timer_stop()
 
 
-for batch, tuning in ((16, 1 << 10), (16, 0), (16, 3 << 10), (32, 0)):
+CASES = [tuple(int(v, 0) for v in a.split(':')) for a in sys.argv[3:]] or [(16, 1 << 10), (16, 0), (16, 3 << 10), (32, 0)]
+for batch, tuning in CASES:
     whole = time_slab(0, grid.dims[2], batch, tuning)
     parts = [time_slab(a, b, batch, tuning) for a, b in pkg.sharding.weighted_slab_ranges(cost, N)]
     print(f"K={batch} tuning={tuning}: whole {whole:.1f} ms, {N} slabs sum {sum(parts):.1f} ms (+{100 * (sum(parts) / whole - 1):.1f} %), "
