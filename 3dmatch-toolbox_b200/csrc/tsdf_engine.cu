@@ -63,8 +63,10 @@ struct tsdf_volume {
   int n_sub = 1;
   cudaStream_t sub_stream[kMaxSub] = {};
   int64_t sub_z[kMaxSub + 1] = {};  // sub-slab i = local planes [sub_z[i], sub_z[i+1])
-  uint2* tile_masks[kMaxSub] = {};  // per sub-slab scratch of the frame-mask pre-pass (tile_mask_kernel)
+  uint2* tile_masks[kMaxSub] = {};  // per sub-slab scratch of the frame-mask pre-pass (non-production variants)
   int64_t tile_mask_cap[kMaxSub] = {};
+  uint2* slot_masks[kSlots] = {};   // whole-slab frame masks of the ring slot's frames (production kernel)
+  int64_t slot_mask_cap = 0;
   int last_slot = -1;
   int64_t ring_pos = 0;
   // surface extraction
@@ -167,6 +169,21 @@ int launch_chunk(tsdf_volume* v, int slot, const float* cam2base, int n) {
     if (v->tuning & 0x200) p.z_reverse = !p.z_reverse;
   }
   const int64_t plane = v->d.dim_x * v->d.dim_y;
+  // frame masks of the whole slab, on the main stream: they are ready before the sub-slab streams get to this
+  // chunk (the main stream runs ahead of the fusion kernels by up to kSlots - 1 chunks)
+  int64_t tiles_per_zgroup = 0;
+  const bool want_masks = v->cull >= 1 && !(v->tuning & (1 << 23));
+  if (want_masks) {
+    if (!v->slot_masks[slot]) {
+      v->slot_mask_cap = tsdf::tile_mask_entries(p.dim_x, p.dim_y, p.nz);
+      CK(cudaMalloc(&v->slot_masks[slot], (size_t)v->slot_mask_cap * sizeof(uint2)));
+    }
+    tsdf::IntegrateParams m = p;
+    m.tile_masks = v->slot_masks[slot];
+    m.tile_mask_cap = v->slot_mask_cap;
+    tiles_per_zgroup = tsdf::launch_tile_masks(m, v->stream);
+    if (tiles_per_zgroup > 0) v->stats.kernel_launches += 1;
+  }
   CK(cudaEventRecord(v->ev_ready[slot], v->stream));
   for (int i = 0; i < v->n_sub; ++i) {
     tsdf::IntegrateParams q = p;
@@ -176,7 +193,11 @@ int launch_chunk(tsdf_volume* v, int slot, const float* cam2base, int n) {
     q.z_begin = (int)(v->d.z_begin + v->sub_z[i]);
     cudaStream_t st = (v->n_sub == 1) ? v->stream : v->sub_stream[i];
     if (v->n_sub > 1) CK(cudaStreamWaitEvent(st, v->ev_ready[slot], 0));
-    if (v->cull >= 1 && !(v->tuning & (1 << 23))) {
+    if (tiles_per_zgroup > 0) {
+      q.tile_masks = v->slot_masks[slot] + (v->sub_z[i] / 8) * tiles_per_zgroup;  // sub-slabs start at multiples of 8 planes
+      q.tile_mask_cap = v->slot_mask_cap - (v->sub_z[i] / 8) * tiles_per_zgroup;
+      q.masks_ready = 1;
+    } else if (want_masks) {
       // scratch for the frame-mask pre-pass; passes of one sub-slab are ordered on its stream, so one buffer each
       if (!v->tile_masks[i]) {
         v->tile_mask_cap[i] = tsdf::tile_mask_entries(q.dim_x, q.dim_y, q.nz);
@@ -398,6 +419,7 @@ void tsdf_destroy(tsdf_volume* v) {
       if (v->ev_join[s][i]) cudaEventDestroy(v->ev_join[s][i]);
   }
   for (int i = 0; i < kMaxSub; ++i) cudaFree(v->tile_masks[i]);
+  for (int s = 0; s < kSlots; ++s) cudaFree(v->slot_masks[s]);
   if (v->owns_volume) { cudaFree(v->tsdf); cudaFree(v->weight); }
   cudaFree(v->tile_offsets);
   cudaFree(v->xyz);

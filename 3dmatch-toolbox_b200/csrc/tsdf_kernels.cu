@@ -1538,6 +1538,21 @@ __global__ void __launch_bounds__(256) selftest_rounding_kernel(unsigned long lo
 
 thread_local int g_integrate_launches = 0;  // kernels the last launch_integrate*() call enqueued
 
+// threads of a warp along x: the power of two in {8, 16, 32} that wastes the fewest lanes.  8 is preferred: a warp
+// then covers 32 x 4 x ZT voxels (128-byte row segments), which keeps thin surface bands and frustum boundaries
+// warp-coherent (measured: 1.2x over 32 x 1 on the 1024^3 workload).
+int choose_lx(int nx_units, int force_lx) {
+  int best_lx = 8;
+  int64_t best_waste = -1;
+  for (int lx = 8; lx <= 32; lx <<= 1) {
+    const int64_t covered = (int64_t)((nx_units + lx - 1) / lx) * lx;
+    const int64_t waste = covered - nx_units;
+    if (best_waste < 0 || waste < best_waste) { best_waste = waste; best_lx = lx; }
+  }
+  if (force_lx == 4 || force_lx == 8 || force_lx == 16 || force_lx == 32) best_lx = force_lx;  // tuning
+  return best_lx;
+}
+
 int ilog2(int v) {
   int s = 0;
   while ((1 << (s + 1)) <= v) ++s;
@@ -1550,17 +1565,7 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
   p.nx_units = p.dim_x / VEC;
   p.lim_x = 0.5f - pixel_round_margin((float)p.im_w, p.cx);
   p.lim_y = 0.5f - pixel_round_margin((float)p.im_h, p.cy);
-  // threads of a warp along x: the power of two in {8, 16, 32} that wastes the fewest lanes.  8 is
-  // preferred: a warp then covers 32 x 4 x ZT voxels (128-byte row segments), which keeps thin surface
-  // bands and frustum boundaries warp-coherent (measured: 1.2x over 32 x 1 on the 1024^3 workload).
-  int best_lx = 8;
-  int64_t best_waste = -1;
-  for (int lx = 8; lx <= 32; lx <<= 1) {
-    const int64_t covered = (int64_t)((p.nx_units + lx - 1) / lx) * lx;
-    const int64_t waste = covered - p.nx_units;
-    if (best_waste < 0 || waste < best_waste) { best_waste = waste; best_lx = lx; }
-  }
-  if (p.force_lx == 4 || p.force_lx == 8 || p.force_lx == 16 || p.force_lx == 32) best_lx = p.force_lx;  // tuning
+  const int best_lx = choose_lx(p.nx_units, p.force_lx);
   p.lx_shift = ilog2(best_lx);
   const int rows = kBlockThreads / best_lx;
   dim3 grid((unsigned)((p.nx_units + best_lx - 1) / best_lx), (unsigned)((p.dim_y + rows - 1) / rows),
@@ -1578,7 +1583,9 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
     bool premask = false;
     if constexpr (!DEVPOSE) {
       const int64_t n_xt = grid.x, n_yt = (int64_t)grid.y * (kBlockThreads / 32), n_tiles = n_xt * n_yt * grid.z;
-      if (packed && p.tile_masks != nullptr && p.cull_level >= 1 && n_tiles <= p.tile_mask_cap) {
+      if (packed && p.tile_masks != nullptr && p.masks_ready && p.cull_level >= 1) {
+        premask = true;  // launch_tile_masks() already filled them for the whole slab (engine, main stream)
+      } else if (packed && p.tile_masks != nullptr && p.cull_level >= 1 && n_tiles <= p.tile_mask_cap) {
         int nf_shift = 0;
         while ((1 << nf_shift) < p.n_frames) ++nf_shift;
         const int64_t threads = ((n_tiles + (32 >> nf_shift) - 1) / (32 >> nf_shift)) * 32;
@@ -1608,6 +1615,33 @@ cudaError_t launch_integrate_t(IntegrateParams p, const float* d_K, const float*
 }  // namespace
 
 int last_integrate_launches() { return g_integrate_launches; }
+
+// Frame masks of EVERY warp tile of the slab described by p (production kernel shape: VEC = 4, ZT = 8), in one
+// launch on stream s.  The engine runs it on its main stream, where it overlaps the previous pass' fusion kernels,
+// and hands each sub-slab launch its z range of the result (tiles are numbered z group-major).  Returns the number
+// of tiles per z group, or 0 when the pre-pass does not apply (the fusion kernel then derives its own masks).
+int64_t launch_tile_masks(IntegrateParams p, cudaStream_t s) {
+  constexpr int VEC = 4, ZT = 8;
+  if (p.dim_x % VEC != 0 || p.variant != 0 || p.cull_level < 1 || p.tile_masks == nullptr || p.no_ptx || p.no_packed ||
+      !p.sanitized || p.fast_level == 0 || !(p.trunc_margin > 0.0f) || (int64_t)p.im_w * p.im_h >= (1 << 22))
+    return 0;
+  p.nx_units = p.dim_x / VEC;
+  p.lim_x = 0.5f - pixel_round_margin((float)p.im_w, p.cx);
+  p.lim_y = 0.5f - pixel_round_margin((float)p.im_h, p.cy);
+  const int lx = choose_lx(p.nx_units, p.force_lx);
+  p.lx_shift = ilog2(lx);
+  const int rows = kBlockThreads / lx;
+  const int64_t n_xt = (p.nx_units + lx - 1) / lx;
+  const int64_t n_yt = (int64_t)((p.dim_y + rows - 1) / rows) * (kBlockThreads / 32);
+  const int64_t n_zg = (p.nz + ZT - 1) / ZT;
+  const int64_t n_tiles = n_xt * n_yt * n_zg;
+  if (n_tiles > p.tile_mask_cap) return 0;
+  int nf_shift = 0;
+  while ((1 << nf_shift) < p.n_frames) ++nf_shift;
+  const int64_t threads = ((n_tiles + (32 >> nf_shift) - 1) / (32 >> nf_shift)) * 32;
+  tile_mask_kernel<VEC, ZT><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p, (int)n_xt, (int)n_yt, n_tiles, nf_shift);
+  return cudaGetLastError() == cudaSuccess ? n_xt * n_yt : 0;
+}
 
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s) {
   if (p.n_frames < 1 || p.n_frames > kMaxBatch) return cudaErrorInvalidValue;

@@ -51,6 +51,7 @@ struct IntegrateParams {
   int no_premask;        // validation: frame masks computed inside the fusion kernel instead of the pre-pass
   uint2* tile_masks;     // scratch for the frame-mask pre-pass (nullptr = none), tile_mask_cap entries
   int64_t tile_mask_cap;
+  int masks_ready;       // tile_masks were filled by launch_tile_masks() for this launch's z range
   int z_reverse;         // dispatch the z groups of the slab in descending order
   int force_lx;          // tuning: threads of a warp laid along x (0 = choose by lane waste)
   int sanitized;         // depth frames went through sanitize_depth_kernel (invalid = -inf)
@@ -84,6 +85,7 @@ constexpr int kExtractTile = 4096;  // voxels per extraction tile (256 threads x
 int64_t tile_mask_entries(int dim_x, int dim_y, int64_t nz);
 cudaError_t launch_fill(float* tsdf, float* weight, int64_t n, cudaStream_t s);
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t s);
+int64_t launch_tile_masks(IntegrateParams p, cudaStream_t s);  // whole-slab mask pre-pass; tiles per z group or 0
 int last_integrate_launches();  // kernels the last launch_integrate*() call of this thread enqueued (1 or 2)
 // Pose and intrinsics read from DEVICE memory (reference-style Integrate argument list).
 cudaError_t launch_integrate_devpose(IntegrateParams p, const float* d_cam_K, const float* d_cam2base,
