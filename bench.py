@@ -52,7 +52,10 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started before the warm-up steps (nvidia-smi takes
+    a few hundred ms to produce its first line, longer than the timed region of a multi-GPU run); mark() is called when
+    the timed region starts and the summary uses the samples taken after it -- or, if the region was too short to
+    catch any, the warm-up samples of the same workload, saying so in "window"."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -61,11 +64,15 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.mark_at = 0
+
+    def mark(self):
+        self.mark_at = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -85,7 +92,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        timed = self.lines[self.mark_at:]
+        window = "timed region" if len(timed) >= 2 else "warm-up + timed region"
+        for line in (timed if len(timed) >= 2 else self.lines):
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
@@ -97,7 +106,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def build_inputs(pkg, cfg, device, rank, world, dist):
@@ -232,13 +242,14 @@ def run_ours(args):
         vol.integrate_batch(depth, poses)
 
     # ---- value: inputs resident in HBM --------------------------------------------------------------
+    sampler = ClockSampler(local_rank)   # every rank watches its own GPU
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)   # every rank watches its own GPU
-    sampler.start()
     vol.reset_stats()
     barrier()
+    sampler.mark()
     vol.timer_start()
     for _ in range(args.steps):
         step_device()
@@ -507,7 +518,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--equal-slabs", action="store_true", help="equal-height z-slabs instead of equal-cost ones")
-    ap.add_argument("--rebalance", type=int, default=4, help="feedback-balancing warm-up steps for N > 1")
+    ap.add_argument("--rebalance", type=int, default=6, help="feedback-balancing warm-up steps for N > 1")
     ap.add_argument("--no-measured-cost", action="store_true",
                     help="N > 1: start from the analytic frustum cost estimate instead of engine-measured plane costs")
     args = ap.parse_args()
