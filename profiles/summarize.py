@@ -41,5 +41,29 @@ def main(rep):
             print(f"    {h.split('stalled_')[1]:28s} {100 * v / tot:5.1f} %")
 
 
+def launches(path):
+    """Share of a step per kernel from an `ncu --metrics gpu__time_duration.sum --csv` launch list."""
+    import collections
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    scale = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[hi + 1:]:
+        if len(r) != len(hdr):
+            continue
+        name = r[kn].split("(")[0].split("::")[-1].split("<")[0]
+        agg[name][0] += 1
+        agg[name][1] += float(r[mv].replace(",", "")) * scale.get(r[mu], 1.0)
+    total = sum(v for _, v in agg.values()) or 1.0
+    print(f"# {path}: per-launch durations under ncu (cold-cache, serialised); share of the summed kernel time")
+    for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:40s} {n:6d} launches {v / 1e3:12.3f} ms {100 * v / total:7.2f} %")
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if sys.argv[1] == "--launches":
+        launches(sys.argv[2])
+    else:
+        main(sys.argv[1])
