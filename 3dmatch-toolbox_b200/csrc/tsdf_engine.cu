@@ -364,7 +364,13 @@ int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
   if (d.stream) {
     v->stream = (cudaStream_t)d.stream;
   } else {
-    e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
+    // The main stream carries the small per-chunk kernels (sanitize, depth pyramids, frame masks) that the sub-slab
+    // fusion launches wait for.  It gets the HIGHEST priority: the block scheduler otherwise serves the thousands of
+    // pending fusion blocks of the previous chunk first, the pre-pass of the next chunk only starts in their tail and
+    // every pass pays its latency chain (~50-100 us, 20 % of a 1/8-slab pass).  tuning bit 25: equal priorities.
+    int prio_lo = 0, prio_hi = 0;
+    if (!(v->tuning & (1 << 25))) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    e = cudaStreamCreateWithPriority(&v->stream, cudaStreamNonBlocking, prio_hi);
     if (e != cudaSuccess) return fail(set_err(TSDF_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)));
     v->owns_stream = true;
   }
