@@ -18,6 +18,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "lib" / "libtsdf_fusion.so"
 
 TSDF_MAX_BATCH = 32
+LEGACY_ENGINE = 1 << 26   # tuning bit without a kernel-variant meaning: any non-zero tuning selects the legacy engine
 
 # every extern "C" symbol include/tsdf_fusion.h declares
 EXPORTED_SYMBOLS = [
@@ -54,18 +55,23 @@ class Stats(C.Structure):
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
-_lib = None
+VALIDATION_LIB_PATH = PKG_DIR / "lib" / "libtsdf_fusion_validation.so"
+_libs = {}
 
 
-def load_library() -> C.CDLL:
-    """dlopen the engine; fails loudly when it has not been built (see __graft_entry__.build)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
-        raise TsdfError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+def load_library(validation: bool = False) -> C.CDLL:
+    """dlopen the engine; fails loudly when it has not been built (see __graft_entry__.build).
+
+    validation=True loads lib/libtsdf_fusion_validation.so: the same library compiled with -DTSDF_VALIDATION, which
+    additionally carries every earlier kernel generation / tuning variant (selected through
+    tsdf_volume_desc.reserved0) for the bit-identity tests.  The shipped library rejects reserved0 != 0."""
+    if validation in _libs:
+        return _libs[validation]
+    path = VALIDATION_LIB_PATH if validation else LIB_PATH
+    if not path.exists():
+        raise TsdfError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU fallback)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     fp, i64p = C.POINTER(C.c_float), C.POINTER(C.c_int64)
     vp = C.c_void_p
     sig = {
@@ -110,7 +116,7 @@ def load_library() -> C.CDLL:
     lib.tsdf_depth_from_u16.restype = None
     lib.tsdf_last_error.restype = C.c_char_p
     lib.tsdf_version.restype = C.c_char_p
-    _lib = lib
+    _libs[validation] = lib
     return lib
 
 
@@ -259,8 +265,11 @@ class Volume:
     """A TSDF volume (or one z-slab of it) resident in the HBM of one GPU."""
 
     def __init__(self, dims, origin, voxel_size, trunc_margin, cam_K, im_size=(640, 480), z_range=None,
-                 device=0, max_batch=0, cull_level=-1, stream=0, ext_tsdf=None, ext_weight=None, tuning=0):
-        self._lib = load_library()
+                 device=0, max_batch=0, cull_level=-1, stream=0, ext_tsdf=None, ext_weight=None, tuning=0,
+                 validation=None):
+        # tuning != 0 selects a kernel variant of the validation flavour of the library (LEGACY_ENGINE = the round-1
+        # per-pass launch sequence with its default kernel)
+        self._lib = load_library(bool(tuning) if validation is None else bool(validation))
         d = VolumeDesc()
         d.dim_x, d.dim_y, d.dim_z = (int(v) for v in dims)
         d.z_begin, d.z_end = (0, d.dim_z) if z_range is None else (int(z_range[0]), int(z_range[1]))
@@ -323,7 +332,9 @@ class Volume:
         if size < n * self.frame_px or poses.size < 16 * n:
             raise ValueError("depth_frames / cam2base smaller than n_frames")
         fn = self._lib.tsdf_integrate_batch_u16 if u16 else self._lib.tsdf_integrate_batch
-        self._keepalive.append((depth_frames, poses))  # async H2D may still read them
+        if len(self._keepalive) >= 64:   # a long loop without synchronize(): wait once instead of growing forever
+            self.synchronize()
+        self._keepalive.append((depth_frames, poses))  # async H2D / the staging kernel may still read them
         _check(fn(self._h, n, _ptr(depth_frames), poses.ctypes.data), "tsdf_integrate_batch")
 
     def download(self, want_tsdf=True, want_weight=True):

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -34,6 +35,35 @@ int set_err(int code, const char* fmt, ...) {
 
 constexpr int kSlots = 3;   // staging ring depth (K-frame depth slots)
 constexpr int kMaxSub = 4;  // concurrent sub-slab streams per handle
+
+// ---- stream engine (tsdf_stream_kernels.cu) ----
+constexpr int kStreamSlots = 2;
+constexpr int kStreamGroupDevice = 1024;  // frames per persistent launch when the input is device-resident
+constexpr int kStreamGroupHost = 128;     // ... when it is host memory (double-buffered against the H2D copies)
+constexpr int kCounterWords = 2 * tsdf::kStreamMaxSegments + 8;  // item_count[], seg_begin[], ticket
+
+// Buffers of one group of frames in flight: the engine's own sanitized copy of the frames, their depth pyramids and
+// poses, and the frame masks / item lists / progress words of the persistent kernel.
+struct StreamSlot {
+  float* depth = nullptr;   int64_t depth_cap = 0;   // frames
+  float* mips = nullptr;    int64_t mips_cap = 0;    // frames
+  uint16_t* mm = nullptr;   int64_t mm_cap = 0;      // frames (raw millimetres, uint16 input)
+  void* pin = nullptr;      size_t pin_cap = 0;      // bytes: pinned staging for pageable host input
+  tsdf::FramePose* poses_dev = nullptr;
+  tsdf::FramePose* poses_pin = nullptr;
+  int64_t poses_cap = 0, poses_pin_cap = 0;          // frames
+  uint2* masks = nullptr;   int64_t masks_cap = 0;   // entries
+  unsigned long long* items = nullptr; int64_t items_cap = 0;
+  unsigned* counters = nullptr;                      // kCounterWords
+  unsigned* progress = nullptr;                      // n_btiles
+  tsdf::StreamJob* job_dev = nullptr;                // [jobs_cap]
+  tsdf::StreamJob* job_pin = nullptr;
+  int jobs_cap = 0;
+  cudaEvent_t ev_copied = nullptr;   // H2D of the group's frames finished
+  cudaEvent_t ev_staged = nullptr;   // the pinned pose / job / frame staging buffers have been consumed
+  cudaEvent_t ev_done = nullptr;     // the group's fusion kernel finished (slot reusable)
+  bool staged = false, busy = false;
+};
 
 }  // namespace
 
@@ -69,6 +99,14 @@ struct tsdf_volume {
   int64_t slot_mask_cap = 0;
   int last_slot = -1;
   int64_t ring_pos = 0;
+  // stream engine
+  bool stream_ok = false;              // the persistent work-list kernel applies to this volume
+  tsdf::StreamLaunch sl = {};          // geometry / intrinsics part of the launch parameters
+  StreamSlot ss[kStreamSlots];
+  int64_t stream_group = 0;
+  unsigned* rec_scratch = nullptr;
+  int resident_blocks = 0;
+  unsigned long long* zcost = nullptr; // per z group: kept (warp tile, frame) pairs since tsdf_reset_stats
   // surface extraction
   unsigned long long* tile_offsets = nullptr;
   int64_t tile_cap = 0;
@@ -308,6 +346,232 @@ int integrate_from_host(tsdf_volume* v, int n_frames, const Src* src, const floa
   return join_substreams(v);
 }
 
+
+// ================================================================================================================
+// Stream engine: groups of frames fused by ONE persistent work-list kernel each (tsdf_stream_kernels.cu).
+// ================================================================================================================
+
+template <typename T>
+int grow(T** ptr, int64_t* cap, int64_t need, bool pinned = false) {
+  if (need <= *cap && *ptr) return TSDF_OK;
+  if (*ptr) {
+    if (pinned) cudaFreeHost(*ptr); else cudaFree(*ptr);   // (cudaFree waits for the work that may still use it)
+    *ptr = nullptr;
+    *cap = 0;
+  }
+  if (pinned) CK(cudaHostAlloc((void**)ptr, (size_t)need * sizeof(T), cudaHostAllocDefault));
+  else CK(cudaMalloc((void**)ptr, (size_t)need * sizeof(T)));
+  *cap = need;
+  return TSDF_OK;
+}
+
+// Conservative margins of the frustum / occlusion tests for a set of poses (see make_cull_margins).
+void stream_cull_margins(float max_abs_corner, const tsdf::FramePose* poses, int64_t n, tsdf::StreamLaunch* L) {
+  float rmax = 1.f, tmax = 0.f;
+  bool finite = true;
+  for (int64_t f = 0; f < n; ++f) {
+    const float* m = &poses[f].m0;
+    for (int i = 0; i < 9; ++i) { rmax = fmaxf(rmax, fabsf(m[i])); finite = finite && std::isfinite(m[i]); }
+    for (int i = 9; i < 12; ++i) { tmax = fmaxf(tmax, fabsf(m[i])); finite = finite && std::isfinite(m[i]); }
+  }
+  const float coord = max_abs_corner + tmax;
+  const float delta = 64.f * FLT_EPSILON * 3.f * rmax * (coord + 1.f);
+  if (!finite || !std::isfinite(delta)) {
+    L->cull_level = 0;
+    L->cull_z = L->cull_gx = L->cull_gy = 0.f;
+    return;
+  }
+  L->cull_z = fmaxf(L->cull_z, 4.f * delta);
+  L->cull_gx = fmaxf(L->cull_gx, 4.f * delta * (fabsf(L->fx) + fabsf(L->cx) + (float)L->im_w + 4.f));
+  L->cull_gy = fmaxf(L->cull_gy, 4.f * delta * (fabsf(L->fy) + fabsf(L->cy) + (float)L->im_h + 4.f));
+}
+
+int stream_init(tsdf_volume* v) {
+  tsdf::StreamLaunch& L = v->sl;
+  memset(&L, 0, sizeof L);
+  L.frame_stride = v->frame_px;
+  L.mip_stride = v->mip.stride;
+  for (int l = 0; l < 5; ++l) { L.mip_w[l] = v->mip.w[l]; L.mip_off[l] = v->mip.off[l]; }
+  L.dim_x = (int)v->d.dim_x; L.dim_y = (int)v->d.dim_y; L.nz = (int)v->nz;
+  L.ox = v->d.origin_x; L.oy = v->d.origin_y; L.oz = v->d.origin_z;
+  L.voxel_size = v->d.voxel_size; L.trunc_margin = v->d.trunc_margin;
+  L.fx = v->d.cam_K[0]; L.cx = v->d.cam_K[2]; L.fy = v->d.cam_K[4]; L.cy = v->d.cam_K[5];
+  L.im_w = v->d.im_width; L.im_h = v->d.im_height;
+  L.chunk = v->batch;
+  v->stream_ok = tsdf::stream_prepare_geometry(&L);
+  // float4 accesses of the slab rows need 16-byte aligned arrays (caller-owned slabs may be offset views)
+  if (((reinterpret_cast<uintptr_t>(v->tsdf) | reinterpret_cast<uintptr_t>(v->weight)) & 15u) != 0) v->stream_ok = false;
+  return TSDF_OK;
+}
+
+int stream_slot_events(StreamSlot& S) {
+  if (!S.ev_copied) CK(cudaEventCreateWithFlags(&S.ev_copied, cudaEventDisableTiming));
+  if (!S.ev_staged) CK(cudaEventCreateWithFlags(&S.ev_staged, cudaEventDisableTiming));
+  if (!S.ev_done) CK(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+  return TSDF_OK;
+}
+
+// Everything a group needs besides the sanitized frames themselves (already in S.depth, produced on `st`):
+// poses on the device, depth pyramids, zeroed counters / progress words.  Fills *job with the device pointers.
+int stream_prepare_job(tsdf_volume* v, StreamSlot& S, int ng, const float* cam2base, tsdf::StreamJob* job,
+                       tsdf::StreamLaunch* L, cudaStream_t st) {
+  const int n_chunks = (ng + L->chunk - 1) / L->chunk;
+  if (int rc = grow(&S.poses_dev, &S.poses_cap, (int64_t)ng)) return rc;
+  if (S.poses_pin_cap < ng) {
+    if (S.staged) CK(cudaEventSynchronize(S.ev_staged));
+    if (int rc = grow(&S.poses_pin, &S.poses_pin_cap, (int64_t)ng, true)) return rc;
+  }
+  if (v->cull >= 2)
+    if (int rc = grow(&S.mips, &S.mips_cap, (int64_t)ng * v->mip.stride)) return rc;
+  if (int rc = grow(&S.masks, &S.masks_cap, (int64_t)n_chunks * L->n_btiles * 8)) return rc;
+  if (int rc = grow(&S.items, &S.items_cap, (int64_t)n_chunks * L->n_btiles)) return rc;
+  if (!S.counters) CK(cudaMalloc(&S.counters, kCounterWords * sizeof(unsigned)));
+  if (!S.progress) CK(cudaMalloc(&S.progress, (size_t)L->n_btiles * sizeof(unsigned)));
+  if (!v->zcost) {
+    CK(cudaMalloc(&v->zcost, (size_t)L->n_zg * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(v->zcost, 0, (size_t)L->n_zg * sizeof(unsigned long long), st));
+  }
+  if (!v->rec_scratch) {
+    v->resident_blocks = tsdf::stream_resident_blocks(v->d.device);
+    if (v->resident_blocks <= 0) return set_err(TSDF_ERR_CUDA, "occupancy query of the fusion kernel failed");
+    CK(cudaMalloc(&v->rec_scratch, (size_t)v->resident_blocks * 8192 * sizeof(unsigned)));
+  }
+  // the pinned pose buffer may still be read by the previous group's copy
+  if (S.staged) CK(cudaEventSynchronize(S.ev_staged));
+  for (int f = 0; f < ng; ++f) pose_from_cam2base(cam2base + 16 * (size_t)f, &S.poses_pin[f]);
+  stream_cull_margins(v->max_abs_corner, S.poses_pin, ng, L);
+  CK(cudaMemcpyAsync(S.poses_dev, S.poses_pin, (size_t)ng * sizeof(tsdf::FramePose), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(S.counters, 0, kCounterWords * sizeof(unsigned), st));
+  CK(cudaMemsetAsync(S.progress, 0, (size_t)L->n_btiles * sizeof(unsigned), st));
+  if (v->cull >= 2) {
+    CK(tsdf::launch_build_depth_mips(S.depth, S.mips, ng, v->d.im_width, v->d.im_height, v->frame_px, st));
+    v->stats.kernel_launches += 1;
+  }
+  memset(job, 0, sizeof *job);
+  job->tsdf = v->tsdf;
+  job->weight = v->weight;
+  job->depth = S.depth;
+  job->mips = (v->cull >= 2) ? S.mips : nullptr;
+  job->poses = S.poses_dev;
+  job->masks = S.masks;
+  job->items = S.items;
+  job->item_count = S.counters;
+  job->progress = S.progress;
+  job->zcost = v->zcost;
+  job->z_begin = (int)v->d.z_begin;
+  return TSDF_OK;
+}
+
+// Launch parameters of a group of `ng` frames for volumes shaped like `v`.
+void stream_group_params(const tsdf_volume* v, int ng, tsdf::StreamLaunch* L) {
+  *L = v->sl;
+  L->n_frames = ng;
+  L->n_chunks = (ng + L->chunk - 1) / L->chunk;
+  L->cull_level = v->cull;
+}
+
+// Frame masks + item lists + the persistent fusion kernel for the jobs described by L (device array L->jobs).
+int stream_launch(tsdf_volume* leader, StreamSlot& S, tsdf::StreamLaunch* L, cudaStream_t st) {
+  L->seg_begin = S.counters + tsdf::kStreamMaxSegments;
+  L->ticket = S.counters + 2 * tsdf::kStreamMaxSegments + 4;
+  L->rec_scratch = leader->rec_scratch;
+  CK(tsdf::launch_stream_masks(*L, st));
+  CK(tsdf::launch_stream_integrate(*L, leader->resident_blocks, st));
+  leader->stats.kernel_launches += 3;
+  return TSDF_OK;
+}
+
+// One group, one volume: S.depth holds the sanitized frames (work queued on v->stream).
+int stream_fuse_group(tsdf_volume* v, StreamSlot& S, int ng, const float* cam2base) {
+  tsdf::StreamLaunch L;
+  stream_group_params(v, ng, &L);
+  if (S.jobs_cap < 1) {
+    CK(cudaMalloc(&S.job_dev, sizeof(tsdf::StreamJob)));
+    CK(cudaHostAlloc((void**)&S.job_pin, sizeof(tsdf::StreamJob), cudaHostAllocDefault));
+    S.jobs_cap = 1;
+  }
+  tsdf::StreamJob job;
+  if (int rc = stream_prepare_job(v, S, ng, cam2base, &job, &L, v->stream)) return rc;
+  {
+    // planes further from the cameras (along z) intersect more of the frusta and cost more: they enter the lists first
+    float tz = 0.f;
+    for (int f = 0; f < ng; ++f) tz += S.poses_pin[f].tz;
+    const float mid = v->d.origin_z + 0.5f * (float)(v->d.z_begin + v->d.z_end) * v->d.voxel_size;
+    L.z_reverse = ((tz / (float)ng) < mid) ? 1 : 0;
+  }
+  *S.job_pin = job;
+  CK(cudaMemcpyAsync(S.job_dev, S.job_pin, sizeof job, cudaMemcpyHostToDevice, v->stream));
+  CK(cudaEventRecord(S.ev_staged, v->stream));
+  S.staged = true;
+  L.jobs = S.job_dev;
+  L.n_jobs = 1;
+  if (int rc = stream_launch(v, S, &L, v->stream)) return rc;
+  CK(cudaEventRecord(S.ev_done, v->stream));
+  S.busy = true;
+  v->stats.frames_integrated += ng;
+  v->n_points = -1;
+  return TSDF_OK;
+}
+
+// Sanitized copy of `ng` frames into S.depth.  Device input: one kernel on v->stream.  Host input: H2D on the copy
+// stream (through the slot's pinned buffer when the source is pageable), then the kernel.
+template <typename Src>
+int stream_stage_frames(tsdf_volume* v, StreamSlot& S, const Src* src, int ng, MemKind kind) {
+  constexpr bool u16 = sizeof(Src) == 2;
+  const int64_t elems = (int64_t)ng * v->frame_px;
+  if (int rc = stream_slot_events(S)) return rc;
+  if (int rc = grow(&S.depth, &S.depth_cap, elems)) return rc;
+  if (kind == MemKind::Device) {
+    if (u16) CK(tsdf::launch_depth_from_u16(reinterpret_cast<const uint16_t*>(src), S.depth, elems, true, v->stream));
+    else CK(tsdf::launch_sanitize_depth(reinterpret_cast<const float*>(src), S.depth, elems, v->stream));
+    v->stats.kernel_launches += 1;
+    return TSDF_OK;
+  }
+  if (!v->copy_stream) CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
+  if (u16)
+    if (int rc = grow(&S.mm, &S.mm_cap, elems)) return rc;
+  // the slot's buffers are overwritten: its previous group must have been fused
+  if (S.busy) CK(cudaStreamWaitEvent(v->copy_stream, S.ev_done, 0));
+  const void* from = src;
+  if (kind == MemKind::PageableHost) {
+    const size_t bytes = (size_t)elems * sizeof(Src);
+    if (S.pin_cap < bytes) {
+      if (S.pin) { CK(cudaStreamSynchronize(v->copy_stream)); cudaFreeHost(S.pin); S.pin = nullptr; S.pin_cap = 0; }
+      CK(cudaHostAlloc(&S.pin, bytes, cudaHostAllocDefault));
+      S.pin_cap = bytes;
+    } else if (S.busy) {
+      CK(cudaEventSynchronize(S.ev_copied));  // the previous H2D out of this pinned buffer
+    }
+    memcpy(S.pin, src, bytes);
+    from = S.pin;
+  }
+  void* to = u16 ? (void*)S.mm : (void*)S.depth;
+  CK(cudaMemcpyAsync(to, from, (size_t)elems * sizeof(Src), cudaMemcpyHostToDevice, v->copy_stream));
+  v->stats.h2d_bytes += elems * (int64_t)sizeof(Src);
+  CK(cudaEventRecord(S.ev_copied, v->copy_stream));
+  CK(cudaStreamWaitEvent(v->stream, S.ev_copied, 0));
+  if (u16) CK(tsdf::launch_depth_from_u16(S.mm, S.depth, elems, true, v->stream));
+  else CK(tsdf::launch_sanitize_depth(S.depth, S.depth, elems, v->stream));
+  v->stats.kernel_launches += 1;
+  return TSDF_OK;
+}
+
+template <typename Src>
+int stream_integrate(tsdf_volume* v, int n_frames, const Src* src, const float* cam2base, MemKind kind) {
+  const int seg_cap = tsdf::kStreamMaxSegments * v->sl.chunk;
+  int group = (kind == MemKind::Device) ? kStreamGroupDevice : kStreamGroupHost;
+  if (group > seg_cap) group = seg_cap;
+  for (int g0 = 0; g0 < n_frames; g0 += group) {
+    const int ng = (n_frames - g0 < group) ? n_frames - g0 : group;
+    // device input is staged and fused in stream order, so one slot suffices; host input alternates two slots so
+    // that the copy of group g + 1 overlaps the fusion of group g
+    StreamSlot& S = v->ss[(kind == MemKind::Device) ? 0 : (int)(v->stream_group++ % kStreamSlots)];
+    if (int rc = stream_stage_frames(v, S, src + (size_t)g0 * v->frame_px, ng, kind)) return rc;
+    if (int rc = stream_fuse_group(v, S, ng, cam2base + 16 * (size_t)g0)) return rc;
+  }
+  return TSDF_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -339,6 +603,8 @@ int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
   if (d.max_batch < 0 || d.max_batch > TSDF_MAX_BATCH) return set_err(TSDF_ERR_ARG, "max_batch out of range");
   if ((d.ext_tsdf == nullptr) != (d.ext_weight == nullptr))
     return set_err(TSDF_ERR_ARG, "ext_tsdf and ext_weight must be given together");
+  if (((reinterpret_cast<uintptr_t>(d.ext_tsdf) | reinterpret_cast<uintptr_t>(d.ext_weight)) & 15u) != 0)
+    return set_err(TSDF_ERR_ARG, "ext_tsdf / ext_weight must be 16-byte aligned (rows are accessed as float4)");
 
   tsdf_volume* v = new (std::nothrow) tsdf_volume();
   if (!v) return set_err(TSDF_ERR_ARG, "out of host memory");
@@ -347,9 +613,19 @@ int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
   v->n_vox = v->nz * d.dim_y * d.dim_x;
   v->frame_px = (int64_t)d.im_width * d.im_height;
   v->mip = tsdf::make_mip_layout(d.im_width, d.im_height);
-  v->batch = d.max_batch ? d.max_batch : 8;   // measured optimum on B200 (K = 4..32 swept, profiles/README.md)
   v->cull = (d.cull_level < 0 || d.cull_level > 2) ? 2 : d.cull_level;
-  v->tuning = d.reserved0;
+#ifdef TSDF_VALIDATION
+  v->tuning = d.reserved0;   // validation flavour of the library: kernel variants / earlier kernel generations
+#else
+  if (d.reserved0 != 0) { delete v; return set_err(TSDF_ERR_ARG, "reserved0 must be 0"); }
+  v->tuning = 0;
+#endif
+  // TSDF_ENGINE=legacy (environment): the round-1 per-pass launch sequence instead of the persistent work-list kernel
+  // (kept for A/B measurements; both are bit-identical)
+  const char* eng = getenv("TSDF_ENGINE");
+  const bool want_legacy = (eng && strcmp(eng, "legacy") == 0) || (v->tuning != 0);
+  // K: frames per chunk of the stream engine (one 32-bit frame mask) / per pass of the legacy launch sequence
+  v->batch = d.max_batch ? d.max_batch : (want_legacy ? 8 : 32);
   {
     const float ex = fmaxf(fabsf(d.origin_x), fabsf(d.origin_x + (float)d.dim_x * d.voxel_size));
     const float ey = fmaxf(fabsf(d.origin_y), fabsf(d.origin_y + (float)d.dim_y * d.voxel_size));
@@ -401,6 +677,7 @@ int tsdf_create(const tsdf_volume_desc* desc, tsdf_volume** out) {
   e = cudaEventCreate(&v->t0);
   if (e == cudaSuccess) e = cudaEventCreate(&v->t1);
   if (e != cudaSuccess) return fail(set_err(TSDF_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)));
+  if (!want_legacy && (rc = stream_init(v)) != TSDF_OK) return fail(rc);
   if (v->owns_volume && (rc = tsdf_reset(v)) != TSDF_OK) return fail(rc);
   *out = v;
   return TSDF_OK;
@@ -424,6 +701,18 @@ void tsdf_destroy(tsdf_volume* v) {
     for (int i = 0; i < kMaxSub; ++i)
       if (v->ev_join[s][i]) cudaEventDestroy(v->ev_join[s][i]);
   }
+  for (StreamSlot& S : v->ss) {
+    cudaFree(S.depth); cudaFree(S.mips); cudaFree(S.mm); cudaFree(S.poses_dev); cudaFree(S.masks); cudaFree(S.items);
+    cudaFree(S.counters); cudaFree(S.progress); cudaFree(S.job_dev);
+    if (S.pin) cudaFreeHost(S.pin);
+    if (S.poses_pin) cudaFreeHost(S.poses_pin);
+    if (S.job_pin) cudaFreeHost(S.job_pin);
+    if (S.ev_copied) cudaEventDestroy(S.ev_copied);
+    if (S.ev_staged) cudaEventDestroy(S.ev_staged);
+    if (S.ev_done) cudaEventDestroy(S.ev_done);
+  }
+  cudaFree(v->rec_scratch);
+  cudaFree(v->zcost);
   for (int i = 0; i < kMaxSub; ++i) cudaFree(v->tile_masks[i]);
   for (int s = 0; s < kSlots; ++s) cudaFree(v->slot_masks[s]);
   if (v->owns_volume) { cudaFree(v->tsdf); cudaFree(v->weight); }
@@ -490,6 +779,7 @@ int tsdf_integrate_batch(tsdf_volume* v, int32_t n_frames, const float* depth_fr
   if (n_frames < 0) return set_err(TSDF_ERR_ARG, "n_frames < 0");
   if (int rc = use_device(v)) return rc;
   const MemKind kind = classify(depth_frames);
+  if (v->stream_ok) return stream_integrate<float>(v, n_frames, depth_frames, cam2base, kind);
   if (kind == MemKind::Device) {
     if (int rc = ensure_ring(v, false)) return rc;
     for (int f0 = 0; f0 < n_frames; f0 += v->batch) {
@@ -512,6 +802,7 @@ int tsdf_integrate_batch_u16(tsdf_volume* v, int32_t n_frames, const uint16_t* d
   if (n_frames < 0) return set_err(TSDF_ERR_ARG, "n_frames < 0");
   if (int rc = use_device(v)) return rc;
   const MemKind kind = classify(depth_mm);
+  if (v->stream_ok) return stream_integrate<uint16_t>(v, n_frames, depth_mm, cam2base, kind);
   if (kind == MemKind::Device) {
     if (int rc = ensure_ring(v, true)) return rc;
     for (int f0 = 0; f0 < n_frames; f0 += v->batch) {
@@ -610,6 +901,10 @@ int tsdf_copy_surface(tsdf_volume* v, float* xyz_host, int64_t capacity_points) 
 int tsdf_surface_device_ptr(tsdf_volume* v, float** xyz_dev, int64_t* n_points) {
   if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
   if (v->n_points < 0) return set_err(TSDF_ERR_STATE, "tsdf_extract_surface has not been called since the last update");
+  // the emit kernel runs on the engine's own (non-blocking) stream: the caller's stream is not ordered after it, so
+  // the buffer is handed out only once it is complete
+  if (int rc = use_device(v)) return rc;
+  CK(cudaStreamSynchronize(v->stream));
   if (xyz_dev) *xyz_dev = v->xyz;
   if (n_points) *n_points = v->n_points;
   return TSDF_OK;

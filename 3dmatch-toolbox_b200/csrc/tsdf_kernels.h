@@ -69,6 +69,56 @@ struct ExtractParams {
   float tsdf_thresh, weight_thresh;
 };
 
+// ---- stream engine (tsdf_stream_kernels.cu): the production fusion path -----------------------------------------
+// A call's frames are cut into CHUNKS of <= kChunkMax consecutive frames (one 32-bit frame mask per warp tile and
+// chunk); a work ITEM is (block tile, chunk).  stream_mask_kernel computes the frame masks of every (warp tile,
+// chunk) of the call up front and appends the non-empty items to per-chunk lists; stream_integrate_kernel is ONE
+// persistent launch that walks those lists chunk after chunk (so the chunk's frames stay L2-resident), with a
+// per-tile progress word ordering the items of one tile.
+constexpr int kChunkMax = 32;
+constexpr int kStreamMaxSegments = 1024;   // jobs x chunks per launch
+
+struct StreamJob {              // device memory; one volume (z-slab) x one group of frames
+  float* tsdf;
+  float* weight;
+  const float* depth;           // sanitized frames of the group, frame f at depth + f * frame_stride
+  const float* mips;            // depth max-pyramids, frame f at mips + f * mip_stride (nullptr: no occlusion test)
+  const FramePose* poses;       // n_frames entries
+  uint2* masks;                 // [n_chunks][n_btiles][8 warps]: {frame mask, interior mask}
+  unsigned long long* items;    // [n_chunks][n_btiles]: block tile | (previous non-empty chunk of the tile + 1) << 32
+  unsigned* item_count;         // [n_chunks], zeroed before stream_mask_kernel
+  unsigned* progress;           // [n_btiles], zeroed per group: (last completed chunk of the tile) + 1
+  unsigned long long* zcost;    // [n_zg] kept (warp tile, frame) pairs per z group, or nullptr
+  int z_begin;                  // global index of the slab's first plane
+  int pad_;
+};
+
+struct StreamLaunch {           // kernel parameter block (constant bank): what every job of the launch shares
+  const StreamJob* jobs;
+  int n_jobs;
+  int n_frames, chunk, n_chunks;      // frames of the group, frames per chunk, chunks
+  unsigned* seg_begin;                // [n_jobs * n_chunks + 1] exclusive prefix of the item counts (segment = job, chunk)
+  unsigned* ticket;                   // item counter of the persistent kernel
+  unsigned* rec_scratch;              // band-voxel records, 8192 per resident block
+  int64_t frame_stride;
+  int mip_stride, mip_w[5], mip_off[5];
+  int dim_x, dim_y, nz, nx_units, lx_shift;
+  int n_xt, n_yb, n_zg, n_btiles;     // block tiles along x, y, z and per slab
+  float ox, oy, oz, voxel_size, trunc_margin;
+  float fx, fy, cx, cy, lim_x, lim_y;
+  int im_w, im_h;
+  int cull_level;
+  float cull_z, cull_gx, cull_gy;
+  int z_reverse;
+};
+
+// Fills the geometry fields of L that follow from dim_x / dim_y / nz (nx_units, lx_shift, n_xt, n_yb, n_zg, n_btiles,
+// lim_x, lim_y).  Returns false when the stream kernels do not apply (dim_x % 4 != 0, image too large, trunc <= 0).
+bool stream_prepare_geometry(StreamLaunch* L);
+int stream_resident_blocks(int device);   // blocks of the persistent kernel that fit the device
+cudaError_t launch_stream_masks(const StreamLaunch& L, cudaStream_t s);      // + segment prefix + ticket reset (2 kernels)
+cudaError_t launch_stream_integrate(const StreamLaunch& L, int n_blocks, cudaStream_t s);
+
 // Bound on |u' - u| between the fast pixel coordinate u' = fma(cam, fx * rcp.approx(z), c0) and the
 // reference's u = fl(fl(fx * fl(cam / z)) + c0) for |u'| <= size + 1.5.  Relative errors: rcp.approx
 // <= 2^-23, every rounded product <= 2^-24, so fl(fx * fl(cam/z)) and cam * fl(fx * rcp(z)) differ by

@@ -1,0 +1,460 @@
+// tsdf_stream_kernels.cu -- the production fusion path: one persistent work-list kernel per group of frames.
+//
+// Replaces depth-fusion/demo.cu:18-68 (Integrate) + the frame loop of demo.cu:156-183 for a whole batch of frames.
+//
+// Work decomposition
+//   * block tile  = 32 x 32 x 8 voxels (x, y, z): 256 threads, each owning 4 consecutive x by 8 consecutive z at one y
+//                   (one float4 of TSDF and of weight per plane); a warp is 8 lanes along x by 4 rows of y.
+//   * chunk       = up to 32 consecutive frames (one 32-bit frame mask per warp tile).
+//   * item        = (block tile, chunk) with at least one frame that can touch the tile.
+//   stream_mask_kernel tests every (warp tile, frame) of the group up front (frustum + hierarchical-Z occlusion,
+//   tsdf_device.cuh) and appends the non-empty items to per-chunk lists.  stream_integrate_kernel is ONE launch of
+//   resident blocks that take items from a global ticket, chunk after chunk, so all blocks work on the same <= 32
+//   depth frames at a time (39 MB: L2-resident) while the volume streams through once per chunk.  Items of one
+//   tile are ordered by a per-tile progress word (release / acquire); items are fetched in ticket order, so the
+//   item waited for is always held by a running block and the wait cannot deadlock.
+//
+// Inside an item
+//   Phase A (per warp, no block barrier): for every frame of the warp tile's mask, the packed bit-exact
+//     classification (voxel_classify_pair) of the thread's 32 voxels.  Certain free-space observations (dist == 1)
+//     only bump an 8-bit pending count per voxel (exact: see apply_pending); a voxel whose observation is NOT certain
+//     (inside the +-trunc band, or pixel rounding within the margin) becomes STICKY for the rest of the item: a
+//     record {owner thread, voxel slot, first uncertain frame f0, pending count so far} is appended to the block's
+//     record list and phase A's further counts for it are ignored.
+//   Write-back: pending counts of the non-sticky voxels, coalesced float4 read-modify-write, once per item.
+//   Phase B (whole block, full lanes): one thread per record loads the voxel's TSDF/weight, applies the pending
+//     count (all older than f0), then evaluates frames f >= f0 of the owner's frame mask with the plain restatement
+//     of the reference (voxel_observation_exact) in ascending order, keeping TSDF/weight in registers; one store.
+//   Every voxel therefore receives exactly the reference's sequence of updates (demo.cu:63-66) in ascending frame
+//   order; there is no barrier per frame and no shared queue traffic per frame.
+#include "tsdf_device.cuh"
+
+namespace tsdf {
+
+namespace {
+
+constexpr int VEC = 4, ZT = 8;
+constexpr int kWarps = kBlockThreads / 32;
+constexpr int kRecCap = kBlockThreads * VEC * ZT;  // every voxel of a block tile becomes sticky at most once per item
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame masks + item lists.  One warp per (job, block tile); lane = frame inside the chunk.  The block tile is
+// tested first (a frame that cannot touch the 32 x 32 x 8 box cannot touch any of its warp tiles), then its 8 warp
+// tiles (32 x 4 x 8).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stream_mask_kernel(const __grid_constant__ StreamLaunch L) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= (int64_t)L.n_jobs * L.n_btiles) return;
+  const int job = (int)(gw / L.n_btiles);
+  int btile = (int)(gw - (int64_t)job * L.n_btiles);
+  if (L.z_reverse) btile = L.n_btiles - 1 - btile;   // far z groups (more of the frusta) enter the lists first
+  const StreamJob& J = L.jobs[job];
+  Intrinsics K;
+  K.fx = L.fx; K.fy = L.fy; K.cx = L.cx; K.cy = L.cy; K.lim_x = L.lim_x; K.lim_y = L.lim_y;
+  const int xt = btile % L.n_xt;
+  const int r = btile / L.n_xt;
+  const int yb = r % L.n_yb, zg = r / L.n_yb;
+  const int rows_per_warp = 32 >> L.lx_shift, rows_per_block = kBlockThreads >> L.lx_shift;
+  const int x_lo = (xt << L.lx_shift) * VEC, x_hi = min(L.dim_x - 1, x_lo + ((VEC << L.lx_shift) - 1));
+  const int yb_lo = yb * rows_per_block, yb_hi = min(L.dim_y - 1, yb_lo + rows_per_block - 1);
+  const int z_lo = J.z_begin + zg * ZT, z_hi = z_lo + ZT - 1;
+  unsigned prev_plus1 = 0u;
+  unsigned long long cost = 0ull;
+  for (int c = 0; c < L.n_chunks; ++c) {
+    const int f = c * L.chunk + lane;
+    const bool valid = lane < L.chunk && f < L.n_frames;
+    unsigned keep_w[kWarps], in_w[kWarps];
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) keep_w[w] = in_w[w] = 0u;
+    if (L.cull_level <= 0) {
+      const unsigned all = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) keep_w[w] = (yb_lo + w * rows_per_warp < L.dim_y) ? all : 0u;
+    } else {
+      FramePose ps = {};
+      const float* mips_f = nullptr;
+      bool bk = false, bi = false;
+      if (valid) {
+        ps = J.poses[f];
+        if (J.mips != nullptr) mips_f = J.mips + (int64_t)f * L.mip_stride;
+        box_frame_test(L, K, ps, mips_f, x_lo, x_hi, yb_lo, yb_hi, z_lo, z_hi, bk, bi);
+      }
+      if (__any_sync(0xffffffffu, bk)) {
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const int y_lo = yb_lo + w * rows_per_warp;
+          bool k = false, i = false;
+          if (bk && y_lo < L.dim_y)
+            box_frame_test(L, K, ps, mips_f, x_lo, x_hi, y_lo, min(L.dim_y - 1, y_lo + rows_per_warp - 1), z_lo, z_hi, k, i);
+          keep_w[w] = __ballot_sync(0xffffffffu, k);
+          in_w[w] = __ballot_sync(0xffffffffu, i);
+        }
+      }
+    }
+    unsigned uni = 0u;
+    uint2* out = J.masks + ((int64_t)c * L.n_btiles + btile) * kWarps;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      uni |= keep_w[w];
+      cost += (unsigned)__popc(keep_w[w]);
+      if (lane == w) out[w] = make_uint2(keep_w[w], in_w[w]);
+    }
+    if (uni != 0u) {
+      if (lane == 0) {
+        const unsigned pos = atomicAdd(&J.item_count[c], 1u);
+        J.items[(int64_t)c * L.n_btiles + pos] = (unsigned long long)(unsigned)btile | ((unsigned long long)prev_plus1 << 32);
+      }
+      prev_plus1 = (unsigned)c + 1u;
+    }
+  }
+  if (lane == 0 && J.zcost != nullptr && cost != 0ull) atomicAdd(&J.zcost[zg], cost);
+}
+
+// Exclusive prefix of the per-(job, chunk) item counts -> seg_begin[0 .. n_seg], and the ticket reset.
+__global__ void __launch_bounds__(kStreamMaxSegments) stream_segment_kernel(const __grid_constant__ StreamLaunch L) {
+  __shared__ unsigned s_warp[kStreamMaxSegments / 32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n_seg = L.n_jobs * L.n_chunks;
+  const unsigned cnt = (t < n_seg) ? L.jobs[t / L.n_chunks].item_count[t % L.n_chunks] : 0u;
+  unsigned incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned v = s_warp[lane], inc2 = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, inc2, d);
+      if (lane >= d) inc2 += u;
+    }
+    s_warp[lane] = inc2 - v;
+  }
+  __syncthreads();
+  const unsigned excl = s_warp[warp] + incl - cnt;
+  if (t < n_seg) L.seg_begin[t] = excl;
+  if (t == n_seg - 1) L.seg_begin[n_seg] = excl + cnt;
+  if (t == 0) *L.ticket = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The persistent fusion kernel.
+// ------------------------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(const __grid_constant__ StreamLaunch L) {
+  __shared__ float4 s_ztab[kChunkMax * ZT];        // plane products M8*t2 of every (frame, plane) of the item
+  __shared__ float4 s_pose[kChunkMax * 3];         // (m0 m1 m2 tx) (m4 m5 m6 ty) (m8 m9 m10 tz) per frame
+  __shared__ unsigned s_pend[ZT][kBlockThreads];   // byte j of [k][t]: pending free-space updates of voxel (j, k) of thread t
+  __shared__ unsigned s_wmask[kWarps];
+  __shared__ unsigned s_rec_count;
+  __shared__ unsigned s_hdr[4];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lx_mask = (1 << L.lx_shift) - 1;
+  const int lx = threadIdx.x & lx_mask, ly = threadIdx.x >> L.lx_shift;
+  const int rows_per_block = kBlockThreads >> L.lx_shift;
+  unsigned* const rec = L.rec_scratch + (size_t)blockIdx.x * kRecCap;
+  Intrinsics K;
+  K.fx = L.fx; K.fy = L.fy; K.cx = L.cx; K.cy = L.cy; K.lim_x = L.lim_x; K.lim_y = L.lim_y;
+  const float im_w_f = (float)L.im_w, half_w = 0.5f * (float)(L.im_w - 1), half_h = 0.5f * (float)(L.im_h - 1);
+  const int64_t plane = (int64_t)L.dim_y * L.dim_x;
+  const unsigned n_seg = (unsigned)(L.n_jobs * L.n_chunks);
+
+  // thread 0: ticket of the next item (fetched one item ahead, so the atomic's latency is off the critical path)
+  unsigned seg = 0u, ticket = 0u, total = 0u;
+  if (threadIdx.x == 0) {
+    ticket = atomicAdd(L.ticket, 1u);
+    total = L.seg_begin[n_seg];
+  }
+
+  for (;;) {
+    if (threadIdx.x == 0) {
+      if (ticket >= total) {
+        s_hdr[0] = 0xffffffffu;
+      } else {
+        while (ticket >= L.seg_begin[seg + 1u]) ++seg;
+        const unsigned job = seg / (unsigned)L.n_chunks, chunk = seg - job * (unsigned)L.n_chunks;
+        const StreamJob& J0 = L.jobs[job];
+        const unsigned long long it = J0.items[(int64_t)chunk * L.n_btiles + (ticket - L.seg_begin[seg])];
+        const unsigned bt = (unsigned)it, need = (unsigned)(it >> 32);
+        s_hdr[0] = job; s_hdr[1] = chunk; s_hdr[2] = bt;
+        // the tile's previous item (an earlier chunk) must be complete: its ticket is smaller than ours, so it is
+        // held by a running block and this wait terminates
+        if (need != 0u)
+          while (ld_acquire(J0.progress + bt) < need) __nanosleep(64);
+        ticket = atomicAdd(L.ticket, 1u);
+      }
+    }
+    __syncthreads();
+    const unsigned job = s_hdr[0];
+    if (job == 0xffffffffu) break;
+    const int chunk = (int)s_hdr[1], btile = (int)s_hdr[2];
+    const StreamJob& J = L.jobs[job];
+    const int xt = btile % L.n_xt;
+    const int rr = btile / L.n_xt;
+    const int yb = rr % L.n_yb, zg = rr / L.n_yb;
+    const int xu = (xt << L.lx_shift) + lx;
+    const int y = yb * rows_per_block + ly;
+    const int zl0 = zg * ZT;
+    const bool active = (xu < L.nx_units) && (y < L.dim_y);
+    const int zcount = min(ZT, L.nz - zl0);
+    const int f_base = chunk * L.chunk;
+    const int nf = min(L.chunk, L.n_frames - f_base);
+    const FramePose* __restrict__ poses = J.poses + f_base;
+
+    const uint2 wm2 = __ldg(J.masks + ((int64_t)chunk * L.n_btiles + btile) * kWarps + warp);
+    const unsigned frame_mask = wm2.x, interior_mask = wm2.y;
+    if (lane == 0) s_wmask[warp] = frame_mask;
+    if (threadIdx.x == 0) s_rec_count = 0u;
+    for (int e = threadIdx.x; e < nf * ZT; e += kBlockThreads) {
+      const int f = e / ZT, k = e - f * ZT;
+      const FramePose ps = poses[f];
+      if (k < 3) {
+        const float4 row = (k == 0) ? make_float4(ps.m0, ps.m1, ps.m2, ps.tx)
+                                    : (k == 1) ? make_float4(ps.m4, ps.m5, ps.m6, ps.ty)
+                                               : make_float4(ps.m8, ps.m9, ps.m10, ps.tz);
+        s_pose[f * 3 + k] = row;
+      }
+      // demo.cu:32,37,39-41: the plane's t2 = base_z - tz and its three products, with the reference's operations
+      const float t2 = __fsub_rn(__fadd_rn(L.oz, __fmul_rn((float)(J.z_begin + zl0 + k), L.voxel_size)), ps.tz);
+      s_ztab[e] = make_float4(__fmul_rn(ps.m8, t2), __fmul_rn(ps.m9, t2), __fmul_rn(ps.m10, t2), 0.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < ZT; ++k) s_pend[k][threadIdx.x] = 0u;
+    __syncthreads();
+
+    const int64_t idx0 = (int64_t)zl0 * plane + (int64_t)y * L.dim_x + (int64_t)xu * VEC;
+    float* const tsdf = J.tsdf;
+    float* const weight = J.weight;
+    const float* const depth0 = J.depth + (int64_t)f_base * L.frame_stride;
+
+    // ---------------- phase A: classification, per warp ----------------
+    unsigned sticky = 0u;  // bit k*VEC + j: voxel handed to phase B
+    if (frame_mask != 0u) {  // warp-uniform
+      const float base_y = __fadd_rn(L.oy, __fmul_rn((float)y, L.voxel_size));  // demo.cu:31
+      for (unsigned fm = frame_mask; fm != 0u; fm &= fm - 1u) {
+        const int f = __ffs(fm) - 1;
+        const float4 p0 = s_pose[f * 3 + 0], p1 = s_pose[f * 3 + 1];
+        // demo.cu:30-41: (M0*t0 + M4*t1) per x; the M8*t2 part comes from s_ztab
+        const float t1 = __fsub_rn(base_y, p1.w);
+        const float yx = __fmul_rn(p1.x, t1), yy = __fmul_rn(p1.y, t1), yz = __fmul_rn(p1.z, t1);
+        float sx[VEC], sy[VEC], sz[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float t0 = __fsub_rn(__fadd_rn(L.ox, __fmul_rn((float)(xu * VEC + j), L.voxel_size)), p0.w);
+          sx[j] = __fadd_rn(__fmul_rn(p0.x, t0), yx);
+          sy[j] = __fadd_rn(__fmul_rn(p0.y, t0), yy);
+          sz[j] = __fadd_rn(__fmul_rn(p0.z, t0), yz);
+        }
+        unsigned exact = 0u;  // bit k*VEC + j: the observation of this frame is not certain
+        if (active) {
+          f32x2_t sx2[2], sy2[2], sz2[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            sx2[h] = pack2(sx[2 * h], sx[2 * h + 1]);
+            sy2[h] = pack2(sy[2 * h], sy[2 * h + 1]);
+            sz2[h] = pack2(sz[2 * h], sz[2 * h + 1]);
+          }
+          // gather base biased by the bit pattern of the rint magic (see voxel_classify_pair)
+          const char* depth_biased =
+              reinterpret_cast<const char*>(depth0 + (int64_t)f * L.frame_stride) - 4ll * (long long)kRintMagicBits;
+          auto plane_body = [&](int k, unsigned& pk, auto interior_tag) {
+            constexpr bool kInterior = decltype(interior_tag)::value;
+            const float4 zt = s_ztab[f * ZT + k];
+            unsigned ex = 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              voxel_classify_pair<kInterior>(sx2[h], sy2[h], sz2[h], zt.x, zt.y, zt.z, K, im_w_f, half_w, half_h,
+                                             depth_biased, L.trunc_margin, 1u << (16 * h), 1u << (16 * h + 8),
+                                             1u << (2 * h), 1u << (2 * h + 1), pk, ex);
+            exact |= ex << (k * VEC);
+          };
+          if ((interior_mask >> f) & 1u) {  // warp-uniform
+#pragma unroll 2
+            for (int k = 0; k < zcount; ++k) {
+              unsigned pk = s_pend[k][threadIdx.x];
+              plane_body(k, pk, std::true_type{});
+              s_pend[k][threadIdx.x] = pk;
+            }
+          } else {
+#pragma unroll 2
+            for (int k = 0; k < zcount; ++k) {
+              unsigned pk = s_pend[k][threadIdx.x];
+              plane_body(k, pk, std::false_type{});
+              s_pend[k][threadIdx.x] = pk;
+            }
+          }
+        }
+        unsigned fresh = exact & ~sticky;
+        if (fresh != 0u) {
+          unsigned pos = atomicAdd(&s_rec_count, (unsigned)__popc(fresh));
+          while (fresh != 0u) {
+            const unsigned s = (unsigned)(__ffs(fresh) - 1);
+            fresh &= fresh - 1u;
+            // free-space observations counted so far are all older than frame f (this frame did not count: the
+            // classification counts only certain observations)
+            const unsigned c = (s_pend[s / VEC][threadIdx.x] >> (8u * (s & (unsigned)(VEC - 1)))) & 0xffu;
+            rec[pos++] = threadIdx.x | (s << 8) | ((unsigned)f << 13) | (c << 18);
+          }
+        }
+        sticky |= exact;
+      }
+
+      // ---------------- write-back of the pending counts (non-sticky voxels), coalesced ----------------
+#pragma unroll 1
+      for (int k = 0; k < ZT; ++k) {
+        unsigned pk = s_pend[k][threadIdx.x];
+        const unsigned st = (sticky >> (k * VEC)) & ((1u << VEC) - 1u);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if ((st >> j) & 1u) pk &= ~(0xffu << (8 * j));
+        if (__any_sync(0xffffffffu, pk != 0u)) {
+          if (active && k < zcount) {
+            float4 T = __ldcg(reinterpret_cast<const float4*>(tsdf + idx0 + k * plane));
+            float4 W = __ldcg(reinterpret_cast<const float4*>(weight + idx0 + k * plane));
+            apply_pending(T.x, W.x, pk & 0xffu);
+            apply_pending(T.y, W.y, (pk >> 8) & 0xffu);
+            apply_pending(T.z, W.z, (pk >> 16) & 0xffu);
+            apply_pending(T.w, W.w, (pk >> 24) & 0xffu);
+            __stcs(reinterpret_cast<float4*>(tsdf + idx0 + k * plane), T);
+            __stcs(reinterpret_cast<float4*>(weight + idx0 + k * plane), W);
+          }
+        }
+      }
+    }
+    __syncthreads();  // records complete; every write-back store of the block precedes phase B's accesses
+
+    // ---------------- phase B: sticky voxels, one record per thread, frames in ascending order ----------------
+    const unsigned n_rec = s_rec_count;
+    for (unsigned base = (unsigned)warp * 32u; base < n_rec; base += kBlockThreads) {  // warp-uniform trip count
+      const unsigned i = base + (unsigned)lane;
+      const bool valid = i < n_rec;
+      unsigned wm = 0u, c = 0u;
+      int64_t idx = 0;
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, t = 0.f, w = 0.f;
+      if (valid) {
+        const unsigned item = __ldcg(rec + i);
+        const int owner_t = (int)(item & 0xffu);
+        const int s = (int)((item >> 8) & 31u), j = s & (VEC - 1), k = s / VEC;
+        const unsigned f0 = (item >> 13) & 31u;
+        c = (item >> 18) & 0xffu;
+        wm = s_wmask[owner_t >> 5] & (0xffffffffu << f0);
+        const int o_xu = (xt << L.lx_shift) + (owner_t & lx_mask);
+        const int o_y = yb * rows_per_block + (owner_t >> L.lx_shift);
+        // voxel centre (demo.cu:30-32), from the GLOBAL indices
+        q0 = __fadd_rn(L.ox, __fmul_rn((float)(o_xu * VEC + j), L.voxel_size));
+        q1 = __fadd_rn(L.oy, __fmul_rn((float)o_y, L.voxel_size));
+        q2 = __fadd_rn(L.oz, __fmul_rn((float)(J.z_begin + zl0 + k), L.voxel_size));
+        idx = ((int64_t)(zl0 + k) * L.dim_y + o_y) * (int64_t)L.dim_x + (int64_t)o_xu * VEC + j;
+        t = __ldcg(tsdf + idx);
+        w = __ldcg(weight + idx);
+        apply_pending(t, w, c);
+      }
+      bool changed = c != 0u;
+      for (unsigned um = __reduce_or_sync(0xffffffffu, wm); um != 0u; um &= um - 1u) {
+        const int f = __ffs(um) - 1;
+        if ((wm >> f) & 1u) {
+          const float4 p0 = s_pose[f * 3 + 0], p1 = s_pose[f * 3 + 1], p2 = s_pose[f * 3 + 2];
+          // demo.cu:35-41, operation for operation
+          const float t0 = __fsub_rn(q0, p0.w), t1 = __fsub_rn(q1, p1.w), t2 = __fsub_rn(q2, p2.w);
+          const float cam_x = __fadd_rn(__fadd_rn(__fmul_rn(p0.x, t0), __fmul_rn(p1.x, t1)), __fmul_rn(p2.x, t2));
+          const float cam_y = __fadd_rn(__fadd_rn(__fmul_rn(p0.y, t0), __fmul_rn(p1.y, t1)), __fmul_rn(p2.y, t2));
+          const float cam_z = __fadd_rn(__fadd_rn(__fmul_rn(p0.z, t0), __fmul_rn(p1.z, t1)), __fmul_rn(p2.z, t2));
+          const float dj = voxel_observation_exact<true, true>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy,
+                                                               depth0 + (int64_t)f * L.frame_stride, L.im_w, L.im_h,
+                                                               L.trunc_margin);
+          if (dj != kNoObservation) {
+            voxel_update(t, w, dj);  // demo.cu:63-66
+            changed = true;
+          }
+        }
+      }
+      if (valid && changed) {
+        __stcg(tsdf + idx, t);
+        __stcg(weight + idx, w);
+      }
+    }
+
+    // ---------------- completion: publish the tile's progress ----------------
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(J.progress + btile, (unsigned)chunk + 1u);
+  }
+}
+
+int g_resident_blocks[64] = {};
+
+}  // namespace
+
+bool stream_prepare_geometry(StreamLaunch* L) {
+  if (L->dim_x % VEC != 0 || !(L->trunc_margin > 0.0f) || (int64_t)L->im_w * L->im_h >= (1 << 22)) return false;
+  if (L->chunk < 1 || L->chunk > kChunkMax) return false;
+  L->nx_units = L->dim_x / VEC;
+  // threads of a warp along x: the power of two in {8, 16, 32} that wastes the fewest lanes (8 preferred, see
+  // choose_lx in tsdf_kernels.cu)
+  int best_lx = 8;
+  int64_t best_waste = -1;
+  for (int lx = 8; lx <= 32; lx <<= 1) {
+    const int64_t waste = (int64_t)((L->nx_units + lx - 1) / lx) * lx - L->nx_units;
+    if (best_waste < 0 || waste < best_waste) { best_waste = waste; best_lx = lx; }
+  }
+  int shift = 0;
+  while ((1 << (shift + 1)) <= best_lx) ++shift;
+  L->lx_shift = shift;
+  const int rows = kBlockThreads / best_lx;
+  L->n_xt = (L->nx_units + best_lx - 1) / best_lx;
+  L->n_yb = (L->dim_y + rows - 1) / rows;
+  L->n_zg = (L->nz + ZT - 1) / ZT;
+  const int64_t nb = (int64_t)L->n_xt * L->n_yb * L->n_zg;
+  if (nb > INT32_MAX / 16) return false;
+  L->n_btiles = (int)nb;
+  L->lim_x = 0.5f - pixel_round_margin((float)L->im_w, L->cx);
+  L->lim_y = 0.5f - pixel_round_margin((float)L->im_h, L->cy);
+  return true;
+}
+
+constexpr int kStreamMinBlocks = 6;
+
+int stream_resident_blocks(int device) {
+  if (device < 0 || device >= 64) return 0;
+  if (g_resident_blocks[device] == 0) {
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_integrate_kernel<kStreamMinBlocks>, kBlockThreads, 0) !=
+            cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+      return 0;
+    g_resident_blocks[device] = per_sm * sms;
+  }
+  return g_resident_blocks[device];
+}
+
+cudaError_t launch_stream_masks(const StreamLaunch& L, cudaStream_t s) {
+  if (L.n_jobs < 1 || L.n_jobs * L.n_chunks > kStreamMaxSegments) return cudaErrorInvalidValue;
+  const int64_t warps = (int64_t)L.n_jobs * L.n_btiles;
+  const int64_t blocks = (warps * 32 + 255) / 256;
+  if (blocks > INT32_MAX) return cudaErrorInvalidConfiguration;
+  stream_mask_kernel<<<(unsigned)blocks, 256, 0, s>>>(L);
+  stream_segment_kernel<<<1, kStreamMaxSegments, 0, s>>>(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stream_integrate(const StreamLaunch& L, int n_blocks, cudaStream_t s) {
+  if (n_blocks < 1) return cudaErrorInvalidValue;
+  stream_integrate_kernel<kStreamMinBlocks><<<n_blocks, kBlockThreads, 0, s>>>(L);
+  return cudaGetLastError();
+}
+
+}  // namespace tsdf

@@ -568,7 +568,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", default="1024", choices=["1024", "512", "demo500", "2048"])
     ap.add_argument("--frames", type=int, default=0, help="override the configuration's frame count")
-    ap.add_argument("--batch", type=int, default=8, help="K: frames fused per pass over the volume")
+    ap.add_argument("--batch", type=int, default=32, help="K: frames per chunk = per pass over the volume (stream engine: 32)")
     ap.add_argument("--cull", type=int, default=2)
     ap.add_argument("--tuning", type=int, default=0, help="kernel tuning variant (bits 0-7) | 256 = exact path only")
     ap.add_argument("--quick", action="store_true", help="value only: skip e2e, K=1 roofline and CPU baseline")

@@ -60,11 +60,12 @@ typedef struct tsdf_volume_desc {
   int32_t im_width, im_height;          /* depth image size (demo.cu:87-88) */
   float cam_K[9];                       /* row-major 3x3 intrinsics (demo.cu:116-117) */
   int32_t device;                       /* CUDA device ordinal */
-  int32_t max_batch;                    /* K: 1..TSDF_MAX_BATCH, 0 = default */
+  int32_t max_batch;                    /* K: frames per chunk (one pass over the volume), 1..TSDF_MAX_BATCH, 0 = default (32) */
   int32_t cull_level;                   /* 0 none, 1 per-thread frustum cull, 2 + per-tile frame mask (default: -1 = 2) */
-  int32_t reserved0;                    /* 0; (internal tuning / validation switches) */
+  int32_t reserved0;                    /* must be 0 */
   void *stream;                         /* cudaStream_t to run on; NULL = the engine creates its own */
-  float *ext_tsdf, *ext_weight;         /* optional caller-owned DEVICE slabs to adopt (NULL = engine-owned) */
+  float *ext_tsdf, *ext_weight;         /* optional caller-owned DEVICE slabs to adopt (NULL = engine-owned);
+                                           16-byte aligned */
 } tsdf_volume_desc;
 
 typedef struct tsdf_stats {
@@ -110,6 +111,9 @@ int tsdf_device_ptrs(tsdf_volume *v, float **tsdf_dev, float **weight_dev);
  * on the device until tsdf_copy_surface. */
 int tsdf_extract_surface(tsdf_volume *v, float tsdf_thresh, float weight_thresh, int64_t *n_points);
 int tsdf_copy_surface(tsdf_volume *v, float *xyz_host, int64_t capacity_points);
+/* Device buffer of the extracted points.  The call waits for the extraction kernels (they run on the engine's own
+ * stream), so the buffer may be read from any stream afterwards; it stays valid until the next tsdf_extract_surface,
+ * integrate, reset or destroy on this handle. */
 int tsdf_surface_device_ptr(tsdf_volume *v, float **xyz_dev, int64_t *n_points);
 
 /* ---- file formats (host) --------------------------------------------------------------------- */

@@ -1,0 +1,139 @@
+"""GPU parity tests of the stream engine (tsdf_stream_kernels.cu: persistent work-list kernel, 32-frame chunks,
+sticky band voxels) through the C ABI: against the CPU oracle on small grids, against the exact-only validation
+kernel and the round-1 launch sequence on grids the oracle would take minutes for."""
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+ORIGIN = (-1.5, -1.5, 0.5)
+
+
+def fuse_gpu(pkg, K, poses, depth, dims, origin, voxel, trunc, **kw):
+    with pkg.Volume(dims, origin, voxel, trunc, K, im_size=(depth.shape[-1], depth.shape[-2]), **kw) as vol:
+        vol.integrate_batch(depth, poses)
+        t, w = vol.download()
+        pts = vol.extract_surface()
+    return t, w, pts
+
+
+@pytest.mark.parametrize("dims,voxel,chunk,cull,n_frames", [
+    ((96, 80, 64), 0.03125, 32, 2, 40),    # two chunks (32 + 8)
+    ((96, 80, 64), 0.03125, 5, 2, 23),     # ragged last chunk
+    ((96, 80, 64), 0.03125, 1, 1, 7),      # one frame per chunk, frustum cull only
+    ((100, 100, 100), 0.03, 32, 0, 33),    # no culling: every frame reaches every tile; partial x tiles
+    ((64, 36, 20), 0.05, 16, 2, 50),       # ragged y tiles and z tail
+    ((32, 32, 8), 0.09, 3, 2, 60),         # ONE block tile, 20 chunks: every item waits for its predecessor
+])
+def test_stream_bit_exact_vs_oracle(pkg, oracle, sequence, dims, voxel, chunk, cull, n_frames):
+    frames = [(7 * i) % 997 for i in range(n_frames)]
+    depth, _, poses, K = sequence(frames)
+    trunc = float(np.float32(voxel) * np.float32(5))
+    t_ref, w_ref = oracle.fuse(K, poses, depth, dims, ORIGIN, voxel, trunc)
+    t, w, pts = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=chunk, cull_level=cull)
+    assert w_ref.max() >= 3
+    assert_bit_equal(w, w_ref, "weights")
+    assert_bit_equal(t, t_ref, "tsdf")
+    assert_bit_equal(pts, oracle.extract_surface(t_ref, w_ref, dims, ORIGIN, voxel), "surface points")
+
+
+def test_stream_equals_exact_only_and_legacy(pkg, sequence):
+    """~2e9 voxel-frames: stream engine (several chunk sizes / cull levels) == every voxel through the plain
+    restatement (validation kernel, tuning bit 8) == the round-1 launch sequence."""
+    frames = list(range(0, 192, 3)) + [500, 640, 777, 901]
+    depth, _, poses, K = sequence(frames)
+    for dims, voxel in [((320, 320, 320), 0.0096), ((512, 256, 128), 0.006)]:
+        trunc = float(np.float32(voxel) * np.float32(5))
+        exact = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=8, cull_level=0, tuning=256)
+        legacy = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=8, cull_level=2,
+                          tuning=pkg.binding.LEGACY_ENGINE)
+        for a, b, name in zip(legacy, exact, ("tsdf", "weight", "points")):
+            assert_bit_equal(a, b, f"legacy {name} dims {dims}")
+        for chunk, cull in [(32, 2), (32, 0), (8, 2), (13, 1), (1, 2)]:
+            got = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=chunk, cull_level=cull)
+            for a, b, name in zip(got, exact, ("tsdf", "weight", "points")):
+                assert_bit_equal(a, b, f"stream {name} chunk={chunk} cull={cull} dims {dims}")
+
+
+def test_stream_groups_and_input_kinds(pkg, oracle, sequence):
+    """300 frames: host input is fused in groups of 128 frames through two alternating slots (H2D overlapped with
+    the fusion of the previous group); pageable, pinned, device float and uint16 inputs must agree bit for bit, also
+    when the frames arrive in several calls."""
+    import torch
+    frames = [(11 * i) % 1000 for i in range(300)]
+    depth, mm, poses, K = sequence(frames)
+    dims, voxel, trunc = (96, 96, 96), 0.03125, 0.15625
+    t_ref, w_ref = oracle.fuse(K, poses, depth, dims, ORIGIN, voxel, trunc)
+    variants = {
+        "pageable": depth,
+        "pinned": torch.from_numpy(depth).pin_memory(),
+        "device": torch.from_numpy(depth).cuda(),
+        "u16 pageable": mm,
+        "u16 pinned": torch.from_numpy(mm.view(np.int16)).pin_memory(),
+        "u16 device": torch.from_numpy(mm.view(np.int16)).cuda(),
+    }
+    for name, src in variants.items():
+        with pkg.Volume(dims, ORIGIN, voxel, trunc, K) as vol:
+            vol.integrate_batch(src, poses)
+            t, w = vol.download()
+        assert_bit_equal(w, w_ref, f"weights [{name}]")
+        assert_bit_equal(t, t_ref, f"tsdf [{name}]")
+    with pkg.Volume(dims, ORIGIN, voxel, trunc, K, max_batch=7) as vol:   # several calls, ragged sizes
+        for a, b in [(0, 1), (1, 130), (130, 131), (131, 300)]:
+            vol.integrate_batch(depth[a:b], poses[a:b])
+        t, w = vol.download()
+    assert_bit_equal(w, w_ref, "weights [4 calls]")
+    assert_bit_equal(t, t_ref, "tsdf [4 calls]")
+
+
+def test_nan_depth_pixels_follow_the_reference(pkg, oracle, sequence):
+    """demo.cu:53-62 does not reject a NaN depth pixel: both comparisons are false and fmin(1.0f, NaN) = 1.0f, so the
+    voxel receives a dist = 1 observation.  Every engine path must do the same (float input; uint16 cannot hold NaN)."""
+    import torch
+    frames = [0, 4, 9, 15, 300]
+    depth, _, poses, K = sequence(frames)
+    depth = depth.copy()
+    rng = np.random.default_rng(11)
+    depth[rng.random(depth.shape) < 0.05] = np.nan
+    depth[2, 100:140, 200:300] = np.nan
+    depth[3, 50:60, 50:60] = np.inf      # +inf IS rejected by the reference (d > 6)
+    depth[3, 70:80, 50:60] = -np.inf
+    for dims, voxel in [((96, 80, 64), 0.03125), ((50, 62, 38), 0.06)]:   # VEC = 4 stream engine / VEC = 1 kernel
+        trunc = float(np.float32(voxel) * np.float32(5))
+        t_ref, w_ref = oracle.fuse(K, poses, depth, dims, ORIGIN, voxel, trunc)
+        if oracle.have_ref_host():
+            t_r, w_r = oracle.ref_host_fuse(K, poses, depth, dims, ORIGIN, voxel, trunc)
+            assert_bit_equal(w_ref, w_r.reshape(w_ref.shape), "oracle vs reference host build (weights)")
+            assert_bit_equal(t_ref, t_r.reshape(t_ref.shape), "oracle vs reference host build (tsdf)")
+        for kw in [dict(), dict(max_batch=2, cull_level=0), dict(tuning=pkg.binding.LEGACY_ENGINE), dict(tuning=256),
+                   dict(tuning=(1 << 22)), dict(tuning=(1 << 20))]:
+            t, w, _ = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, **kw)
+            assert_bit_equal(w, w_ref, f"weights {dims} {kw}")
+            assert_bit_equal(t, t_ref, f"tsdf {dims} {kw}")
+        # the reference-shaped entry point reads the caller's frame in place (not sanitized)
+        n = dims[0] * dims[1] * dims[2]
+        t_dev = torch.ones(n, dtype=torch.float32, device="cuda")
+        w_dev = torch.zeros(n, dtype=torch.float32, device="cuda")
+        K_dev = torch.from_numpy(K).cuda()
+        for f in range(len(frames)):
+            pkg.Integrate(K_dev, torch.from_numpy(poses[f]).cuda(), torch.from_numpy(depth[f]).cuda(), 480, 640,
+                          dims[0], dims[1], dims[2], *ORIGIN, voxel, trunc, t_dev, w_dev,
+                          stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert_bit_equal(w_dev.cpu().numpy().reshape(w_ref.shape), w_ref, f"tsdf_Integrate weights {dims}")
+        assert_bit_equal(t_dev.cpu().numpy().reshape(t_ref.shape), t_ref, f"tsdf_Integrate tsdf {dims}")
+
+
+def test_misaligned_external_slab_is_rejected(pkg, synth):
+    import torch
+    buf = torch.zeros(64 * 64 * 64 + 4, dtype=torch.float32, device="cuda")
+    ok = torch.zeros(64 * 64 * 64, dtype=torch.float32, device="cuda")
+    with pytest.raises(pkg.TsdfError, match="16-byte aligned"):
+        pkg.Volume((64, 64, 64), ORIGIN, 0.05, 0.25, synth.CAM_K, ext_tsdf=buf[1:], ext_weight=ok)
+
+
+def test_shipped_library_rejects_reserved0(pkg, synth):
+    with pytest.raises(pkg.TsdfError, match="reserved0"):
+        pkg.Volume((64, 64, 64), ORIGIN, 0.05, 0.25, synth.CAM_K, tuning=5, validation=False)
