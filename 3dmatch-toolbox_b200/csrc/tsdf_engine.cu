@@ -434,7 +434,7 @@ int stream_prepare_job(tsdf_volume* v, StreamSlot& S, int ng, const float* cam2b
   if (!v->rec_scratch) {
     v->resident_blocks = tsdf::stream_resident_blocks(v->d.device);
     if (v->resident_blocks <= 0) return set_err(TSDF_ERR_CUDA, "occupancy query of the fusion kernel failed");
-    CK(cudaMalloc(&v->rec_scratch, (size_t)v->resident_blocks * 8192 * sizeof(unsigned)));
+    CK(cudaMalloc(&v->rec_scratch, (size_t)v->resident_blocks * 2 * 8192 * sizeof(unsigned)));
   }
   // the pinned pose buffer may still be read by the previous group's copy
   if (S.staged) CK(cudaEventSynchronize(S.ev_staged));
@@ -481,15 +481,23 @@ int stream_launch(tsdf_volume* leader, StreamSlot& S, tsdf::StreamLaunch* L, cud
   return TSDF_OK;
 }
 
+int stream_job_array(StreamSlot& S, int n) {
+  if (S.jobs_cap >= n) return TSDF_OK;
+  if (S.staged) CK(cudaEventSynchronize(S.ev_staged));
+  if (S.job_dev) { cudaFree(S.job_dev); S.job_dev = nullptr; }
+  if (S.job_pin) { cudaFreeHost(S.job_pin); S.job_pin = nullptr; }
+  S.jobs_cap = 0;
+  CK(cudaMalloc(&S.job_dev, (size_t)n * sizeof(tsdf::StreamJob)));
+  CK(cudaHostAlloc((void**)&S.job_pin, (size_t)n * sizeof(tsdf::StreamJob), cudaHostAllocDefault));
+  S.jobs_cap = n;
+  return TSDF_OK;
+}
+
 // One group, one volume: S.depth holds the sanitized frames (work queued on v->stream).
 int stream_fuse_group(tsdf_volume* v, StreamSlot& S, int ng, const float* cam2base) {
   tsdf::StreamLaunch L;
   stream_group_params(v, ng, &L);
-  if (S.jobs_cap < 1) {
-    CK(cudaMalloc(&S.job_dev, sizeof(tsdf::StreamJob)));
-    CK(cudaHostAlloc((void**)&S.job_pin, sizeof(tsdf::StreamJob), cudaHostAllocDefault));
-    S.jobs_cap = 1;
-  }
+  if (int rc = stream_job_array(S, 1)) return rc;
   tsdf::StreamJob job;
   if (int rc = stream_prepare_job(v, S, ng, cam2base, &job, &L, v->stream)) return rc;
   {
@@ -1007,6 +1015,219 @@ int tsdf_point_cloud_to_tdf(const float* pts, int64_t n_pts, const int32_t dims[
   }
   cudaFree(d_pts); cudaFree(d_occ); cudaFree(d_tdf);
   return rc;
+}
+
+int tsdf_integrate_multi(tsdf_volume* const* vols, int32_t n_vols, int32_t n_frames, const void* const* frames,
+                         int32_t frames_are_u16, const float* const* cam2base) {
+  if (!vols || !frames || !cam2base || n_vols < 1) return set_err(TSDF_ERR_ARG, "bad argument");
+  if (n_frames < 0) return set_err(TSDF_ERR_ARG, "n_frames < 0");
+  for (int i = 0; i < n_vols; ++i)
+    if (!vols[i] || !frames[i] || !cam2base[i]) return set_err(TSDF_ERR_ARG, "NULL entry %d", i);
+  if (n_frames == 0) return TSDF_OK;
+  tsdf_volume* lead = vols[0];
+  bool same = lead->stream_ok;
+  for (int i = 1; i < n_vols && same; ++i) {
+    const tsdf_volume* v = vols[i];
+    same = v->stream_ok && v->d.device == lead->d.device && v->d.dim_x == lead->d.dim_x && v->d.dim_y == lead->d.dim_y &&
+           v->nz == lead->nz && v->d.origin_x == lead->d.origin_x && v->d.origin_y == lead->d.origin_y &&
+           v->d.origin_z == lead->d.origin_z && v->d.voxel_size == lead->d.voxel_size &&
+           v->d.trunc_margin == lead->d.trunc_margin && v->d.im_width == lead->d.im_width &&
+           v->d.im_height == lead->d.im_height && memcmp(v->d.cam_K, lead->d.cam_K, sizeof lead->d.cam_K) == 0 &&
+           v->batch == lead->batch && v->cull == lead->cull;
+    for (int j = 0; j < i && same; ++j) same = vols[j] != v;
+  }
+  const int n_chunks = (n_frames + lead->batch - 1) / lead->batch;
+  if (!same || n_vols == 1 || (int64_t)n_vols * n_chunks > tsdf::kStreamMaxSegments || n_frames > kStreamGroupDevice) {
+    // not one launch's worth of identical volumes: one call per volume (still asynchronous, on each volume's stream)
+    for (int i = 0; i < n_vols; ++i) {
+      const int rc = frames_are_u16 ? tsdf_integrate_batch_u16(vols[i], n_frames, (const uint16_t*)frames[i], cam2base[i])
+                                    : tsdf_integrate_batch(vols[i], n_frames, (const float*)frames[i], cam2base[i]);
+      if (rc) return rc;
+    }
+    return TSDF_OK;
+  }
+  if (int rc = use_device(lead)) return rc;
+  tsdf::StreamLaunch L;
+  stream_group_params(lead, n_frames, &L);
+  StreamSlot& LS = lead->ss[0];
+  if (int rc = stream_slot_events(LS)) return rc;
+  if (int rc = stream_job_array(LS, n_vols)) return rc;
+  if (LS.staged) CK(cudaEventSynchronize(LS.ev_staged));   // the pinned job array may still be read
+  float tz = 0.f;
+  for (int i = 0; i < n_vols; ++i) {
+    tsdf_volume* v = vols[i];
+    StreamSlot& S = v->ss[0];
+    const MemKind kind = classify(frames[i]);
+    // staging and the per-volume pre-pass run on the volume's own stream (after whatever is queued there, e.g. a
+    // reset); the leader's stream waits for it
+    int rc = frames_are_u16 ? stream_stage_frames<uint16_t>(v, S, (const uint16_t*)frames[i], n_frames, kind)
+                            : stream_stage_frames<float>(v, S, (const float*)frames[i], n_frames, kind);
+    if (rc) return rc;
+    if ((rc = stream_prepare_job(v, S, n_frames, cam2base[i], &LS.job_pin[i], &L, v->stream))) return rc;
+    CK(cudaEventRecord(S.ev_staged, v->stream));
+    S.staged = true;
+    if (v != lead) CK(cudaStreamWaitEvent(lead->stream, S.ev_staged, 0));
+    for (int f = 0; f < n_frames; ++f) tz += S.poses_pin[f].tz;
+    v->stats.frames_integrated += n_frames;
+    v->n_points = -1;
+  }
+  if (!lead->rec_scratch) return set_err(TSDF_ERR_STATE, "record scratch missing");
+  {
+    const float mid = lead->d.origin_z + 0.5f * (float)(lead->d.z_begin + lead->d.z_end) * lead->d.voxel_size;
+    L.z_reverse = ((tz / ((float)n_frames * (float)n_vols)) < mid) ? 1 : 0;
+  }
+  CK(cudaMemcpyAsync(LS.job_dev, LS.job_pin, (size_t)n_vols * sizeof(tsdf::StreamJob), cudaMemcpyHostToDevice, lead->stream));
+  CK(cudaEventRecord(LS.ev_staged, lead->stream));
+  LS.staged = true;
+  L.jobs = LS.job_dev;
+  L.n_jobs = n_vols;
+  // (the item counters / segment table / ticket of the launch are the leader's)
+  if (int rc = stream_launch(lead, LS, &L, lead->stream)) return rc;
+  CK(cudaEventRecord(LS.ev_done, lead->stream));
+  LS.busy = true;
+  for (int i = 1; i < n_vols; ++i) {
+    tsdf_volume* v = vols[i];
+    CK(cudaStreamWaitEvent(v->stream, LS.ev_done, 0));
+    CK(cudaEventRecord(v->ss[0].ev_done, v->stream));
+    v->ss[0].busy = true;
+  }
+  return TSDF_OK;
+}
+
+int tsdf_get_z_cost(tsdf_volume* v, uint64_t* cost, int32_t n_groups) {
+  if (!v || !cost) return set_err(TSDF_ERR_ARG, "NULL argument");
+  const int64_t n = (v->nz + 7) / 8;
+  if (n_groups < n) return set_err(TSDF_ERR_ARG, "cost holds %d groups, the slab has %lld", n_groups, (long long)n);
+  if (int rc = tsdf_synchronize(v)) return rc;
+  if (!v->zcost) {
+    memset(cost, 0, (size_t)n * sizeof *cost);
+    return TSDF_OK;
+  }
+  CK(cudaMemcpy(cost, v->zcost, (size_t)n * sizeof *cost, cudaMemcpyDeviceToHost));
+  return TSDF_OK;
+}
+
+int tsdf_plan_z_cost(const tsdf_volume_desc* desc, int32_t n_frames, const void* frames, int32_t frames_are_u16,
+                     const float* cam2base, int32_t frame_step, uint64_t* cost, int32_t n_groups) {
+  if (!desc || !frames || !cam2base || !cost || n_frames < 1) return set_err(TSDF_ERR_ARG, "bad argument");
+  if (frame_step < 1) frame_step = 1;
+  const int64_t groups = (desc->dim_z + 7) / 8;
+  if (n_groups < groups) return set_err(TSDF_ERR_ARG, "cost holds %d groups, the grid has %lld", n_groups, (long long)groups);
+  CK(cudaSetDevice(desc->device));
+  tsdf::StreamLaunch L;
+  memset(&L, 0, sizeof L);
+  const tsdf::MipLayout mip = tsdf::make_mip_layout(desc->im_width, desc->im_height);
+  const int64_t px = (int64_t)desc->im_width * desc->im_height;
+  L.frame_stride = px;
+  L.mip_stride = mip.stride;
+  for (int l = 0; l < 5; ++l) { L.mip_w[l] = mip.w[l]; L.mip_off[l] = mip.off[l]; }
+  L.dim_x = (int)desc->dim_x; L.dim_y = (int)desc->dim_y; L.nz = (int)desc->dim_z;
+  L.ox = desc->origin_x; L.oy = desc->origin_y; L.oz = desc->origin_z;
+  L.voxel_size = desc->voxel_size; L.trunc_margin = desc->trunc_margin;
+  L.fx = desc->cam_K[0]; L.cx = desc->cam_K[2]; L.fy = desc->cam_K[4]; L.cy = desc->cam_K[5];
+  L.im_w = desc->im_width; L.im_h = desc->im_height;
+  L.chunk = tsdf::kChunkMax;
+  L.cull_level = (desc->cull_level < 0 || desc->cull_level > 2) ? 2 : desc->cull_level;
+  if (!tsdf::stream_prepare_geometry(&L)) {
+    // the stream kernels do not apply to this grid: uniform cost (equal-height slabs)
+    for (int64_t g = 0; g < groups; ++g) cost[g] = 1;
+    return TSDF_OK;
+  }
+  const int ns = (n_frames + frame_step - 1) / frame_step;
+  L.n_frames = ns;
+  L.n_chunks = (ns + L.chunk - 1) / L.chunk;
+  L.n_jobs = 1;
+  std::vector<tsdf::FramePose> poses((size_t)ns);
+  for (int i = 0; i < ns; ++i) pose_from_cam2base(cam2base + 16 * (size_t)i * frame_step, &poses[i]);
+  {
+    const float ex = fmaxf(fabsf(desc->origin_x), fabsf(desc->origin_x + (float)desc->dim_x * desc->voxel_size));
+    const float ey = fmaxf(fabsf(desc->origin_y), fabsf(desc->origin_y + (float)desc->dim_y * desc->voxel_size));
+    const float ez = fmaxf(fabsf(desc->origin_z), fabsf(desc->origin_z + (float)desc->dim_z * desc->voxel_size));
+    stream_cull_margins(fmaxf(ex, fmaxf(ey, ez)), poses.data(), ns, &L);
+  }
+  float *d_depth = nullptr, *d_mips = nullptr;
+  uint16_t* d_mm = nullptr;
+  tsdf::FramePose* d_poses = nullptr;
+  tsdf::StreamJob* d_job = nullptr;
+  unsigned long long* d_cost = nullptr;
+  cudaStream_t st = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_depth); cudaFree(d_mips); cudaFree(d_mm); cudaFree(d_poses); cudaFree(d_job); cudaFree(d_cost);
+    if (st) cudaStreamDestroy(st);
+  };
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&d_depth, (size_t)ns * px * sizeof(float));
+  if (e == cudaSuccess && L.cull_level >= 2) e = cudaMalloc(&d_mips, (size_t)ns * mip.stride * sizeof(float));
+  if (e == cudaSuccess && frames_are_u16) e = cudaMalloc(&d_mm, (size_t)px * sizeof(uint16_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_poses, (size_t)ns * sizeof(tsdf::FramePose));
+  if (e == cudaSuccess) e = cudaMalloc(&d_job, sizeof(tsdf::StreamJob));
+  if (e == cudaSuccess) e = cudaMalloc(&d_cost, (size_t)groups * sizeof(unsigned long long));
+  const MemKind kind = classify(frames);
+  for (int i = 0; i < ns && e == cudaSuccess; ++i) {
+    const size_t off = (size_t)i * frame_step * px;
+    float* dst = d_depth + (size_t)i * px;
+    if (frames_are_u16) {
+      const uint16_t* src = (const uint16_t*)frames + off;
+      if (kind != MemKind::Device) {
+        e = cudaMemcpyAsync(d_mm, src, (size_t)px * sizeof(uint16_t), cudaMemcpyHostToDevice, st);
+        src = d_mm;
+      }
+      if (e == cudaSuccess) e = tsdf::launch_depth_from_u16(src, dst, px, true, st);
+    } else {
+      const float* src = (const float*)frames + off;
+      if (kind != MemKind::Device) {
+        e = cudaMemcpyAsync(dst, src, (size_t)px * sizeof(float), cudaMemcpyHostToDevice, st);
+        src = dst;
+      }
+      if (e == cudaSuccess) e = tsdf::launch_sanitize_depth(src, dst, px, st);
+    }
+  }
+  if (e == cudaSuccess && L.cull_level >= 2)
+    e = tsdf::launch_build_depth_mips(d_depth, d_mips, ns, desc->im_width, desc->im_height, px, st);
+  tsdf::StreamJob job;
+  memset(&job, 0, sizeof job);
+  job.depth = d_depth;
+  job.mips = (L.cull_level >= 2) ? d_mips : nullptr;
+  job.poses = d_poses;
+  job.zcost = d_cost;
+  job.z_begin = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_poses, poses.data(), (size_t)ns * sizeof(tsdf::FramePose), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_job, &job, sizeof job, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_cost, 0, (size_t)groups * sizeof(unsigned long long), st);
+  L.jobs = d_job;
+  if (e == cudaSuccess) e = tsdf::launch_stream_cost(L, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cost, d_cost, (size_t)groups * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) return set_err(TSDF_ERR_CUDA, "tsdf_plan_z_cost: %s", cudaGetErrorString(e));
+  return TSDF_OK;
+}
+
+int tsdf_split_slabs(const uint64_t* cost, int32_t n_groups, int64_t dim_z, int32_t n_slabs, double base_cost,
+                     int64_t* z_cuts) {
+  if (!cost || !z_cuts || n_groups < 1 || n_slabs < 1 || dim_z < 1) return set_err(TSDF_ERR_ARG, "bad argument");
+  if ((dim_z + 7) / 8 != n_groups) return set_err(TSDF_ERR_ARG, "n_groups must be ceil(dim_z / 8)");
+  if (n_slabs > n_groups) return set_err(TSDF_ERR_ARG, "more slabs than groups of 8 planes");
+  // cost of a group = its kept (tile, frame) pairs + base_cost x the mean (culled tiles are cheap, not free)
+  double mean = 0;
+  for (int g = 0; g < n_groups; ++g) mean += (double)cost[g];
+  mean /= n_groups;
+  std::vector<double> cum((size_t)n_groups + 1, 0.0);
+  for (int g = 0; g < n_groups; ++g) cum[g + 1] = cum[g] + (double)cost[g] + base_cost * mean + 1e-9;
+  z_cuts[0] = 0;
+  int g = 0;
+  for (int r = 1; r < n_slabs; ++r) {
+    const double target = cum[n_groups] * r / n_slabs;
+    while (g < n_groups && cum[g + 1] <= target) ++g;
+    // the cut nearer to the target, keeping at least one group per slab on both sides
+    int cut = (g < n_groups && target - cum[g] > cum[g + 1] - target) ? g + 1 : g;
+    const int lo = (int)(z_cuts[r - 1] / 8) + 1, hi = n_groups - (n_slabs - r);
+    if (cut < lo) cut = lo;
+    if (cut > hi) cut = hi;
+    z_cuts[r] = (int64_t)cut * 8;
+  }
+  z_cuts[n_slabs] = dim_z;
+  return TSDF_OK;
 }
 
 int tsdf_selftest_rounding(int32_t device, int64_t* mismatches) {

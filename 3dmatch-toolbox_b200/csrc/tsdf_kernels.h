@@ -97,9 +97,10 @@ struct StreamLaunch {           // kernel parameter block (constant bank): what 
   const StreamJob* jobs;
   int n_jobs;
   int n_frames, chunk, n_chunks;      // frames of the group, frames per chunk, chunks
+  int epoch;                          // frames per epoch (phase A / phase B alternation inside a chunk)
   unsigned* seg_begin;                // [n_jobs * n_chunks + 1] exclusive prefix of the item counts (segment = job, chunk)
   unsigned* ticket;                   // item counter of the persistent kernel
-  unsigned* rec_scratch;              // band-voxel records, 8192 per resident block
+  unsigned* rec_scratch;              // sticky-voxel records, 2 x 8192 per resident block
   int64_t frame_stride;
   int mip_stride, mip_w[5], mip_off[5];
   int dim_x, dim_y, nz, nx_units, lx_shift;
@@ -118,6 +119,8 @@ bool stream_prepare_geometry(StreamLaunch* L);
 int stream_resident_blocks(int device);   // blocks of the persistent kernel that fit the device
 cudaError_t launch_stream_masks(const StreamLaunch& L, cudaStream_t s);      // + segment prefix + ticket reset (2 kernels)
 cudaError_t launch_stream_integrate(const StreamLaunch& L, int n_blocks, cudaStream_t s);
+// Only the per-z-group work counts (jobs[].zcost) of the frames in L; no masks, no item lists (slab planning).
+cudaError_t launch_stream_cost(const StreamLaunch& L, cudaStream_t s);
 
 // Bound on |u' - u| between the fast pixel coordinate u' = fma(cam, fx * rcp.approx(z), c0) and the
 // reference's u = fl(fl(fx * fl(cam / z)) + c0) for |u'| <= size + 1.5.  Relative errors: rcp.approx

@@ -29,6 +29,8 @@
 //   order; there is no barrier per frame and no shared queue traffic per frame.
 #include "tsdf_device.cuh"
 
+#include <cstdlib>
+
 namespace tsdf {
 
 namespace {
@@ -36,6 +38,24 @@ namespace {
 constexpr int VEC = 4, ZT = 8;
 constexpr int kWarps = kBlockThreads / 32;
 constexpr int kRecCap = kBlockThreads * VEC * ZT;  // every voxel of a block tile becomes sticky at most once per item
+
+// Exactly rounded packed fp32 operations with a scalar (broadcast) second operand.  The explicit .rn forms are never
+// contracted into a fused multiply-add, so mul2s followed by add2s is two roundings, like __fmul_rn / __fadd_rn.
+__device__ __forceinline__ f32x2_t sub2s(f32x2_t a, float s) {
+  f32x2_t r;
+  asm("{\n\t.reg .b64 b;\n\tmov.b64 b, {%2, %2};\n\tsub.rn.f32x2 %0, %1, b;\n\t}" : "=l"(r) : "l"(a), "f"(s));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2s(f32x2_t a, float s) {
+  f32x2_t r;
+  asm("{\n\t.reg .b64 b;\n\tmov.b64 b, {%2, %2};\n\tmul.rn.f32x2 %0, %1, b;\n\t}" : "=l"(r) : "l"(a), "f"(s));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add2s(f32x2_t a, float s) {
+  f32x2_t r;
+  asm("{\n\t.reg .b64 b;\n\tmov.b64 b, {%2, %2};\n\tadd.rn.f32x2 %0, %1, b;\n\t}" : "=l"(r) : "l"(a), "f"(s));
+  return r;
+}
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -51,6 +71,8 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 // tested first (a frame that cannot touch the 32 x 32 x 8 box cannot touch any of its warp tiles), then its 8 warp
 // tiles (32 x 4 x 8).
 // ------------------------------------------------------------------------------------------------
+// kCostOnly: no masks / items are written, only the per-z-group counts of kept (warp tile, frame) pairs (slab planning).
+template <bool kCostOnly>
 __global__ void __launch_bounds__(256) stream_mask_kernel(const __grid_constant__ StreamLaunch L) {
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -102,19 +124,23 @@ __global__ void __launch_bounds__(256) stream_mask_kernel(const __grid_constant_
       }
     }
     unsigned uni = 0u;
-    uint2* out = J.masks + ((int64_t)c * L.n_btiles + btile) * kWarps;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
       uni |= keep_w[w];
       cost += (unsigned)__popc(keep_w[w]);
-      if (lane == w) out[w] = make_uint2(keep_w[w], in_w[w]);
     }
-    if (uni != 0u) {
-      if (lane == 0) {
-        const unsigned pos = atomicAdd(&J.item_count[c], 1u);
-        J.items[(int64_t)c * L.n_btiles + pos] = (unsigned long long)(unsigned)btile | ((unsigned long long)prev_plus1 << 32);
+    if constexpr (!kCostOnly) {
+      uint2* out = J.masks + ((int64_t)c * L.n_btiles + btile) * kWarps;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w)
+        if (lane == w) out[w] = make_uint2(keep_w[w], in_w[w]);
+      if (uni != 0u) {
+        if (lane == 0) {
+          const unsigned pos = atomicAdd(&J.item_count[c], 1u);
+          J.items[(int64_t)c * L.n_btiles + pos] = (unsigned long long)(unsigned)btile | ((unsigned long long)prev_plus1 << 32);
+        }
+        prev_plus1 = (unsigned)c + 1u;
       }
-      prev_plus1 = (unsigned)c + 1u;
     }
   }
   if (lane == 0 && J.zcost != nullptr && cost != 0ull) atomicAdd(&J.zcost[zg], cost);
@@ -159,14 +185,14 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
   __shared__ float4 s_pose[kChunkMax * 3];         // (m0 m1 m2 tx) (m4 m5 m6 ty) (m8 m9 m10 tz) per frame
   __shared__ unsigned s_pend[ZT][kBlockThreads];   // byte j of [k][t]: pending free-space updates of voxel (j, k) of thread t
   __shared__ unsigned s_wmask[kWarps];
-  __shared__ unsigned s_rec_count;
+  __shared__ unsigned s_rec_count[3];              // record counters, rotating over the epochs
   __shared__ unsigned s_hdr[4];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lx_mask = (1 << L.lx_shift) - 1;
   const int lx = threadIdx.x & lx_mask, ly = threadIdx.x >> L.lx_shift;
   const int rows_per_block = kBlockThreads >> L.lx_shift;
-  unsigned* const rec = L.rec_scratch + (size_t)blockIdx.x * kRecCap;
+  unsigned* const rec_base = L.rec_scratch + (size_t)blockIdx.x * (2 * kRecCap);  // two lists, alternating epochs
   Intrinsics K;
   K.fx = L.fx; K.fy = L.fy; K.cx = L.cx; K.cy = L.cy; K.lim_x = L.lim_x; K.lim_y = L.lim_y;
   const float im_w_f = (float)L.im_w, half_w = 0.5f * (float)(L.im_w - 1), half_h = 0.5f * (float)(L.im_h - 1);
@@ -218,7 +244,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
     const uint2 wm2 = __ldg(J.masks + ((int64_t)chunk * L.n_btiles + btile) * kWarps + warp);
     const unsigned frame_mask = wm2.x, interior_mask = wm2.y;
     if (lane == 0) s_wmask[warp] = frame_mask;
-    if (threadIdx.x == 0) s_rec_count = 0u;
+    if (threadIdx.x == 0) s_rec_count[0] = s_rec_count[1] = s_rec_count[2] = 0u;
     for (int e = threadIdx.x; e < nf * ZT; e += kBlockThreads) {
       const int f = e / ZT, k = e - f * ZT;
       const FramePose ps = poses[f];
@@ -241,32 +267,50 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
     float* const weight = J.weight;
     const float* const depth0 = J.depth + (int64_t)f_base * L.frame_stride;
 
-    // ---------------- phase A: classification, per warp ----------------
-    unsigned sticky = 0u;  // bit k*VEC + j: voxel handed to phase B
-    if (frame_mask != 0u) {  // warp-uniform
-      const float base_y = __fadd_rn(L.oy, __fmul_rn((float)y, L.voxel_size));  // demo.cu:31
-      for (unsigned fm = frame_mask; fm != 0u; fm &= fm - 1u) {
+    // voxel-centre coordinates of the thread's patch (demo.cu:30-31), from the GLOBAL indices; x as f32x2 pairs
+    const float base_y = __fadd_rn(L.oy, __fmul_rn((float)y, L.voxel_size));
+    f32x2_t bx2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      bx2[h] = pack2(__fadd_rn(L.ox, __fmul_rn((float)(xu * VEC + 2 * h), L.voxel_size)),
+                     __fadd_rn(L.ox, __fmul_rn((float)(xu * VEC + 2 * h + 1), L.voxel_size)));
+
+    unsigned block_mask = 0u;
+#pragma unroll
+    for (int w8 = 0; w8 < kWarps; ++w8) block_mask |= s_wmask[w8];
+
+    // The chunk is walked in EPOCHS of L.epoch frames: phase A (classification, per warp) of the epoch's frames, then
+    // phase B (exact evaluation of the voxels that became sticky in this epoch, whole block), then the sticky marks are
+    // dropped.  A voxel flagged only because its pixel rounding was within the margin at one frame therefore costs at
+    // most one epoch of exact evaluations, while voxels inside the +-trunc band are simply flagged again.
+    // One barrier per epoch: the record lists alternate between two buffers and the counters rotate over three words,
+    // so a warp that has finished its share of phase B goes straight on to the next epoch's phase A.
+    unsigned n_epoch = 0u;
+    for (int e0 = 0; e0 < nf; e0 += L.epoch) {
+      const unsigned epoch_bits = ((L.epoch >= 32) ? 0xffffffffu : ((1u << L.epoch) - 1u)) << e0;
+      if ((block_mask & epoch_bits) == 0u) continue;  // block-uniform
+      const unsigned slot = n_epoch % 3u;
+      unsigned* const rec = rec_base + (n_epoch & 1u) * kRecCap;
+      ++n_epoch;
+
+      // ---------------- phase A: classification, per warp ----------------
+      unsigned sticky = 0u;  // bit k*VEC + j: voxel handed to phase B of this epoch
+      for (unsigned fm = frame_mask & epoch_bits; fm != 0u; fm &= fm - 1u) {
         const int f = __ffs(fm) - 1;
         const float4 p0 = s_pose[f * 3 + 0], p1 = s_pose[f * 3 + 1];
-        // demo.cu:30-41: (M0*t0 + M4*t1) per x; the M8*t2 part comes from s_ztab
+        // demo.cu:35-41: (M0*t0 + M4*t1) per x with the reference's operations (one rounding each; the packed
+        // mul.rn / add.rn forms are exactly rounded per lane and never contracted); the M8*t2 part comes from s_ztab
         const float t1 = __fsub_rn(base_y, p1.w);
         const float yx = __fmul_rn(p1.x, t1), yy = __fmul_rn(p1.y, t1), yz = __fmul_rn(p1.z, t1);
-        float sx[VEC], sy[VEC], sz[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const float t0 = __fsub_rn(__fadd_rn(L.ox, __fmul_rn((float)(xu * VEC + j), L.voxel_size)), p0.w);
-          sx[j] = __fadd_rn(__fmul_rn(p0.x, t0), yx);
-          sy[j] = __fadd_rn(__fmul_rn(p0.y, t0), yy);
-          sz[j] = __fadd_rn(__fmul_rn(p0.z, t0), yz);
-        }
         unsigned exact = 0u;  // bit k*VEC + j: the observation of this frame is not certain
         if (active) {
           f32x2_t sx2[2], sy2[2], sz2[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            sx2[h] = pack2(sx[2 * h], sx[2 * h + 1]);
-            sy2[h] = pack2(sy[2 * h], sy[2 * h + 1]);
-            sz2[h] = pack2(sz[2 * h], sz[2 * h + 1]);
+            const f32x2_t t0 = sub2s(bx2[h], p0.w);
+            sx2[h] = add2s(mul2s(t0, p0.x), yx);
+            sy2[h] = add2s(mul2s(t0, p0.y), yy);
+            sz2[h] = add2s(mul2s(t0, p0.z), yz);
           }
           // gather base biased by the bit pattern of the rint magic (see voxel_classify_pair)
           const char* depth_biased =
@@ -300,11 +344,11 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
         }
         unsigned fresh = exact & ~sticky;
         if (fresh != 0u) {
-          unsigned pos = atomicAdd(&s_rec_count, (unsigned)__popc(fresh));
+          unsigned pos = atomicAdd(&s_rec_count[slot], (unsigned)__popc(fresh));
           while (fresh != 0u) {
             const unsigned s = (unsigned)(__ffs(fresh) - 1);
             fresh &= fresh - 1u;
-            // free-space observations counted so far are all older than frame f (this frame did not count: the
+            // the free-space observations counted so far are all older than frame f (this frame did not count: the
             // classification counts only certain observations)
             const unsigned c = (s_pend[s / VEC][threadIdx.x] >> (8u * (s & (unsigned)(VEC - 1)))) & 0xffu;
             rec[pos++] = threadIdx.x | (s << 8) | ((unsigned)f << 13) | (c << 18);
@@ -312,15 +356,85 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
         }
         sticky |= exact;
       }
+      // the sticky voxels' counts now belong to their records (and whatever phase A counted for them after f0 is
+      // void): restart them
+      if (sticky != 0u) {
+#pragma unroll
+        for (int k = 0; k < ZT; ++k) {
+          const unsigned st = (sticky >> (k * VEC)) & ((1u << VEC) - 1u);
+          if (st != 0u) {
+            unsigned keep = 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+              if ((st >> j) & 1u) keep &= ~(0xffu << (8 * j));
+            s_pend[k][threadIdx.x] &= keep;
+          }
+        }
+      }
+      __syncthreads();  // the epoch's records are complete
 
-      // ---------------- write-back of the pending counts (non-sticky voxels), coalesced ----------------
+      // ---------------- phase B: sticky voxels, one record per thread, frames in ascending order ----------------
+      const unsigned n_rec = s_rec_count[slot];
+      // the counter of the epoch after the next one: last read in the previous epoch's phase B, i.e. before this barrier;
+      // first written after the next epoch's barrier
+      if (threadIdx.x == 0) s_rec_count[(slot + 2u) % 3u] = 0u;
+      for (unsigned base = (unsigned)warp * 32u; base < n_rec; base += kBlockThreads) {  // warp-uniform trip count
+        const unsigned i = base + (unsigned)lane;
+        const bool valid = i < n_rec;
+        unsigned wm = 0u, c = 0u;
+        int64_t idx = 0;
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, t = 0.f, w = 0.f;
+        if (valid) {
+          const unsigned item = __ldcg(rec + i);
+          const int owner_t = (int)(item & 0xffu);
+          const int s = (int)((item >> 8) & 31u), j = s & (VEC - 1), k = s / VEC;
+          const unsigned f0 = (item >> 13) & 31u;
+          c = (item >> 18) & 0xffu;
+          wm = s_wmask[owner_t >> 5] & (0xffffffffu << f0) & epoch_bits;
+          const int o_xu = (xt << L.lx_shift) + (owner_t & lx_mask);
+          const int o_y = yb * rows_per_block + (owner_t >> L.lx_shift);
+          // voxel centre (demo.cu:30-32), from the GLOBAL indices
+          q0 = __fadd_rn(L.ox, __fmul_rn((float)(o_xu * VEC + j), L.voxel_size));
+          q1 = __fadd_rn(L.oy, __fmul_rn((float)o_y, L.voxel_size));
+          q2 = __fadd_rn(L.oz, __fmul_rn((float)(J.z_begin + zl0 + k), L.voxel_size));
+          idx = ((int64_t)(zl0 + k) * L.dim_y + o_y) * (int64_t)L.dim_x + (int64_t)o_xu * VEC + j;
+          t = __ldcg(tsdf + idx);
+          w = __ldcg(weight + idx);
+          apply_pending(t, w, c);
+        }
+        bool changed = c != 0u;
+        for (unsigned um = __reduce_or_sync(0xffffffffu, wm); um != 0u; um &= um - 1u) {
+          const int f = __ffs(um) - 1;
+          if ((wm >> f) & 1u) {
+            const float4 p0 = s_pose[f * 3 + 0], p1 = s_pose[f * 3 + 1], p2 = s_pose[f * 3 + 2];
+            // demo.cu:35-41, operation for operation
+            const float t0 = __fsub_rn(q0, p0.w), t1 = __fsub_rn(q1, p1.w), t2 = __fsub_rn(q2, p2.w);
+            const float cam_x = __fadd_rn(__fadd_rn(__fmul_rn(p0.x, t0), __fmul_rn(p1.x, t1)), __fmul_rn(p2.x, t2));
+            const float cam_y = __fadd_rn(__fadd_rn(__fmul_rn(p0.y, t0), __fmul_rn(p1.y, t1)), __fmul_rn(p2.y, t2));
+            const float cam_z = __fadd_rn(__fadd_rn(__fmul_rn(p0.z, t0), __fmul_rn(p1.z, t1)), __fmul_rn(p2.z, t2));
+            const float dj = voxel_observation_exact<true, true>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy,
+                                                                 depth0 + (int64_t)f * L.frame_stride, L.im_w, L.im_h,
+                                                                 L.trunc_margin);
+            if (dj != kNoObservation) {
+              voxel_update(t, w, dj);  // demo.cu:63-66
+              changed = true;
+            }
+          }
+        }
+        if (valid && changed) {
+          __stcg(tsdf + idx, t);
+          __stcg(weight + idx, w);
+        }
+      }
+    }
+    __syncthreads();  // every phase B store of the block precedes the write-back's loads
+
+    // ---------------- write-back of the pending counts (certain free-space observations), coalesced ----------------
+    // (after the last phase B: the float4 rows are re-read here, so they carry phase B's stores)
+    if (frame_mask != 0u) {  // warp-uniform
 #pragma unroll 1
       for (int k = 0; k < ZT; ++k) {
-        unsigned pk = s_pend[k][threadIdx.x];
-        const unsigned st = (sticky >> (k * VEC)) & ((1u << VEC) - 1u);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j)
-          if ((st >> j) & 1u) pk &= ~(0xffu << (8 * j));
+        const unsigned pk = s_pend[k][threadIdx.x];
         if (__any_sync(0xffffffffu, pk != 0u)) {
           if (active && k < zcount) {
             float4 T = __ldcg(reinterpret_cast<const float4*>(tsdf + idx0 + k * plane));
@@ -333,58 +447,6 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
             __stcs(reinterpret_cast<float4*>(weight + idx0 + k * plane), W);
           }
         }
-      }
-    }
-    __syncthreads();  // records complete; every write-back store of the block precedes phase B's accesses
-
-    // ---------------- phase B: sticky voxels, one record per thread, frames in ascending order ----------------
-    const unsigned n_rec = s_rec_count;
-    for (unsigned base = (unsigned)warp * 32u; base < n_rec; base += kBlockThreads) {  // warp-uniform trip count
-      const unsigned i = base + (unsigned)lane;
-      const bool valid = i < n_rec;
-      unsigned wm = 0u, c = 0u;
-      int64_t idx = 0;
-      float q0 = 0.f, q1 = 0.f, q2 = 0.f, t = 0.f, w = 0.f;
-      if (valid) {
-        const unsigned item = __ldcg(rec + i);
-        const int owner_t = (int)(item & 0xffu);
-        const int s = (int)((item >> 8) & 31u), j = s & (VEC - 1), k = s / VEC;
-        const unsigned f0 = (item >> 13) & 31u;
-        c = (item >> 18) & 0xffu;
-        wm = s_wmask[owner_t >> 5] & (0xffffffffu << f0);
-        const int o_xu = (xt << L.lx_shift) + (owner_t & lx_mask);
-        const int o_y = yb * rows_per_block + (owner_t >> L.lx_shift);
-        // voxel centre (demo.cu:30-32), from the GLOBAL indices
-        q0 = __fadd_rn(L.ox, __fmul_rn((float)(o_xu * VEC + j), L.voxel_size));
-        q1 = __fadd_rn(L.oy, __fmul_rn((float)o_y, L.voxel_size));
-        q2 = __fadd_rn(L.oz, __fmul_rn((float)(J.z_begin + zl0 + k), L.voxel_size));
-        idx = ((int64_t)(zl0 + k) * L.dim_y + o_y) * (int64_t)L.dim_x + (int64_t)o_xu * VEC + j;
-        t = __ldcg(tsdf + idx);
-        w = __ldcg(weight + idx);
-        apply_pending(t, w, c);
-      }
-      bool changed = c != 0u;
-      for (unsigned um = __reduce_or_sync(0xffffffffu, wm); um != 0u; um &= um - 1u) {
-        const int f = __ffs(um) - 1;
-        if ((wm >> f) & 1u) {
-          const float4 p0 = s_pose[f * 3 + 0], p1 = s_pose[f * 3 + 1], p2 = s_pose[f * 3 + 2];
-          // demo.cu:35-41, operation for operation
-          const float t0 = __fsub_rn(q0, p0.w), t1 = __fsub_rn(q1, p1.w), t2 = __fsub_rn(q2, p2.w);
-          const float cam_x = __fadd_rn(__fadd_rn(__fmul_rn(p0.x, t0), __fmul_rn(p1.x, t1)), __fmul_rn(p2.x, t2));
-          const float cam_y = __fadd_rn(__fadd_rn(__fmul_rn(p0.y, t0), __fmul_rn(p1.y, t1)), __fmul_rn(p2.y, t2));
-          const float cam_z = __fadd_rn(__fadd_rn(__fmul_rn(p0.z, t0), __fmul_rn(p1.z, t1)), __fmul_rn(p2.z, t2));
-          const float dj = voxel_observation_exact<true, true>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy,
-                                                               depth0 + (int64_t)f * L.frame_stride, L.im_w, L.im_h,
-                                                               L.trunc_margin);
-          if (dj != kNoObservation) {
-            voxel_update(t, w, dj);  // demo.cu:63-66
-            changed = true;
-          }
-        }
-      }
-      if (valid && changed) {
-        __stcg(tsdf + idx, t);
-        __stcg(weight + idx, w);
       }
     }
 
@@ -402,6 +464,11 @@ int g_resident_blocks[64] = {};
 bool stream_prepare_geometry(StreamLaunch* L) {
   if (L->dim_x % VEC != 0 || !(L->trunc_margin > 0.0f) || (int64_t)L->im_w * L->im_h >= (1 << 22)) return false;
   if (L->chunk < 1 || L->chunk > kChunkMax) return false;
+  if (L->epoch < 1) L->epoch = 8;
+  if (const char* e = getenv("TSDF_STREAM_EPOCH")) {   // tuning / A-B measurements
+    const int v = atoi(e);
+    if (v >= 1 && v <= kChunkMax) L->epoch = v;
+  }
   L->nx_units = L->dim_x / VEC;
   // threads of a warp along x: the power of two in {8, 16, 32} that wastes the fewest lanes (8 preferred, see
   // choose_lx in tsdf_kernels.cu)
@@ -426,16 +493,29 @@ bool stream_prepare_geometry(StreamLaunch* L) {
   return true;
 }
 
-constexpr int kStreamMinBlocks = 6;
+// Resident blocks per SM the kernel is compiled for: 6 (40 registers), 5 (48) or 4 (64).  TSDF_STREAM_MINB in the
+// environment overrides the default for A/B measurements.
+int stream_min_blocks() {
+  static int minb = 0;
+  if (minb == 0) {
+    minb = 5;
+    if (const char* e = getenv("TSDF_STREAM_MINB")) {
+      const int v = atoi(e);
+      if (v == 4 || v == 5 || v == 6) minb = v;
+    }
+  }
+  return minb;
+}
 
 int stream_resident_blocks(int device) {
   if (device < 0 || device >= 64) return 0;
   if (g_resident_blocks[device] == 0) {
     int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_integrate_kernel<kStreamMinBlocks>, kBlockThreads, 0) !=
-            cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
-      return 0;
+    const int minb = stream_min_blocks();
+    cudaError_t e = (minb == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_integrate_kernel<4>, kBlockThreads, 0)
+                  : (minb == 5) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_integrate_kernel<5>, kBlockThreads, 0)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_integrate_kernel<6>, kBlockThreads, 0);
+    if (e != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
     g_resident_blocks[device] = per_sm * sms;
   }
   return g_resident_blocks[device];
@@ -446,14 +526,26 @@ cudaError_t launch_stream_masks(const StreamLaunch& L, cudaStream_t s) {
   const int64_t warps = (int64_t)L.n_jobs * L.n_btiles;
   const int64_t blocks = (warps * 32 + 255) / 256;
   if (blocks > INT32_MAX) return cudaErrorInvalidConfiguration;
-  stream_mask_kernel<<<(unsigned)blocks, 256, 0, s>>>(L);
+  stream_mask_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(L);
   stream_segment_kernel<<<1, kStreamMaxSegments, 0, s>>>(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stream_cost(const StreamLaunch& L, cudaStream_t s) {
+  if (L.n_jobs < 1) return cudaErrorInvalidValue;
+  const int64_t blocks = ((int64_t)L.n_jobs * L.n_btiles * 32 + 255) / 256;
+  if (blocks > INT32_MAX) return cudaErrorInvalidConfiguration;
+  stream_mask_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(L);
   return cudaGetLastError();
 }
 
 cudaError_t launch_stream_integrate(const StreamLaunch& L, int n_blocks, cudaStream_t s) {
   if (n_blocks < 1) return cudaErrorInvalidValue;
-  stream_integrate_kernel<kStreamMinBlocks><<<n_blocks, kBlockThreads, 0, s>>>(L);
+  switch (stream_min_blocks()) {
+    case 4: stream_integrate_kernel<4><<<n_blocks, kBlockThreads, 0, s>>>(L); break;
+    case 5: stream_integrate_kernel<5><<<n_blocks, kBlockThreads, 0, s>>>(L); break;
+    default: stream_integrate_kernel<6><<<n_blocks, kBlockThreads, 0, s>>>(L); break;
+  }
   return cudaGetLastError();
 }
 

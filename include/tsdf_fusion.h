@@ -100,6 +100,28 @@ int tsdf_integrate_batch(tsdf_volume *v, int32_t n_frames, const float *depth_fr
  * exactly as ReadDepth does (utils.hpp:82-84). */
 int tsdf_integrate_batch_u16(tsdf_volume *v, int32_t n_frames, const uint16_t *depth_mm, const float *cam2base);
 
+/* n_vols independent volumes (fragments, fuseSceneFragments.m:36-81) of identical shape on ONE device, each with
+ * its own frames and poses, fused by one launch: frames[i] = n_frames depth frames of volume i (float metres or, with
+ * frames_are_u16, raw uint16 millimetres; host or device), cam2base[i] = [n_frames][16] on the host.  Small volumes
+ * then fill the GPU together instead of one after the other.  Results are identical to n_vols tsdf_integrate_batch
+ * calls (to which the call falls back when the volumes differ in shape). */
+int tsdf_integrate_multi(tsdf_volume *const *vols, int32_t n_vols, int32_t n_frames, const void *const *frames,
+                         int32_t frames_are_u16, const float *const *cam2base);
+
+/* ---- z-slab planning (multi-GPU) ----------------------------------------------- */
+/* Work estimate per group of 8 z-planes of the WHOLE grid of `desc` (its z range and device memory are not used)
+ * for a frame sequence: the number of (32x4x8-voxel tile, frame) pairs that survive the frustum and occlusion culls,
+ * i.e. what the fusion kernel has to classify.  Every frame_step-th frame is sampled.  cost: ceil(dim_z / 8) entries.
+ * Deterministic (integer counts), so every rank of a multi-process run derives the same partition. */
+int tsdf_plan_z_cost(const tsdf_volume_desc *desc, int32_t n_frames, const void *frames, int32_t frames_are_u16,
+                     const float *cam2base, int32_t frame_step, uint64_t *cost, int32_t n_groups);
+/* The same counts as accumulated by a handle's own fusion calls since tsdf_create (its slab only). */
+int tsdf_get_z_cost(tsdf_volume *v, uint64_t *cost, int32_t n_groups);
+/* n_slabs contiguous z-slabs of (nearly) equal summed cost, cut at multiples of 8 planes: z_cuts[0] = 0 ...
+ * z_cuts[n_slabs] = dim_z.  base_cost: cost of a fully culled group relative to the mean group (0.05 is typical). */
+int tsdf_split_slabs(const uint64_t *cost, int32_t n_groups, int64_t dim_z, int32_t n_slabs, double base_cost,
+                     int64_t *z_cuts);
+
 /* ---- results --------------------------------------------------------------------------------- */
 /* Device->host copy of the slab (demo.cu:186-187).  Either pointer may be NULL. */
 int tsdf_download(tsdf_volume *v, float *tsdf_host, float *weight_host);
