@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "tsdf_read_depth_png", "tsdf_read_depth_png_u16", "tsdf_depth_from_u16", "tsdf_multiply_matrix",
     "tsdf_invert_matrix", "tsdf_Integrate", "tsdf_SaveVoxelGrid2SurfacePointCloud", "tsdf_last_error",
     "tsdf_version", "tsdf_device_count", "tsdf_selftest_rounding", "tsdf_ComputeTDF", "tsdf_tdf_grid_from_points",
-    "tsdf_point_cloud_to_tdf",
+    "tsdf_point_cloud_to_tdf", "tsdf_integrate_multi", "tsdf_plan_z_cost", "tsdf_get_z_cost", "tsdf_split_slabs",
 ]
 
 
@@ -101,6 +101,10 @@ def load_library(validation: bool = False) -> C.CDLL:
         "tsdf_ComputeTDF": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp],
         "tsdf_tdf_grid_from_points": [vp, C.c_int64, C.c_float, C.c_int32, vp, vp],
         "tsdf_point_cloud_to_tdf": [vp, C.c_int64, vp, vp, C.c_float, C.c_float, vp],
+        "tsdf_integrate_multi": [vp, C.c_int32, C.c_int32, vp, C.c_int32, vp],
+        "tsdf_plan_z_cost": [C.POINTER(VolumeDesc), C.c_int32, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32],
+        "tsdf_get_z_cost": [vp, vp, C.c_int32],
+        "tsdf_split_slabs": [vp, C.c_int32, C.c_int64, C.c_int32, C.c_double, vp],
         "tsdf_device_count": [C.POINTER(C.c_int32)],
         "tsdf_selftest_rounding": [C.c_int32, i64p],
     }
@@ -247,6 +251,77 @@ def point_cloud_to_tdf(pts, dims, origin, voxel_size=0.01, trunc_margin=0.05) ->
     return out
 
 
+def _frames_arg(depth_frames):
+    """(object to keep alive, address, is_u16, element count) of a numpy array / torch tensor of depth frames."""
+    if isinstance(depth_frames, np.ndarray):
+        u16 = depth_frames.dtype == np.uint16
+        a = np.ascontiguousarray(depth_frames, dtype=np.uint16 if u16 else np.float32)
+        return a, int(a.ctypes.data), u16, a.size
+    import torch
+    u16 = depth_frames.dtype in (torch.uint16, torch.int16)
+    if not depth_frames.is_contiguous():
+        raise ValueError("depth tensor must be contiguous")
+    return depth_frames, int(depth_frames.data_ptr()), u16, depth_frames.numel()
+
+
+def make_desc(dims, origin, voxel_size, trunc_margin, cam_K, im_size=(640, 480), z_range=None, device=0, max_batch=0,
+              cull_level=-1, tuning=0) -> VolumeDesc:
+    d = VolumeDesc()
+    d.dim_x, d.dim_y, d.dim_z = (int(v) for v in dims)
+    d.z_begin, d.z_end = (0, d.dim_z) if z_range is None else (int(z_range[0]), int(z_range[1]))
+    d.origin_x, d.origin_y, d.origin_z = (float(v) for v in origin)
+    d.voxel_size, d.trunc_margin = float(voxel_size), float(trunc_margin)
+    d.im_width, d.im_height = int(im_size[0]), int(im_size[1])
+    d.cam_K = (C.c_float * 9)(*[float(v) for v in np.asarray(cam_K, np.float32).ravel()])
+    d.device, d.max_batch, d.cull_level = int(device), int(max_batch), int(cull_level)
+    d.reserved0 = int(tuning)
+    return d
+
+
+def plan_z_cost(dims, origin, voxel_size, trunc_margin, cam_K, depth_frames, cam2base, im_size=(640, 480), device=0,
+                frame_step=1, cull_level=-1) -> np.ndarray:
+    """Work per group of 8 z-planes of the whole grid for a frame sequence (tsdf_plan_z_cost): uint64 [ceil(dz / 8)]."""
+    d = make_desc(dims, origin, voxel_size, trunc_margin, cam_K, im_size, device=device, cull_level=cull_level)
+    keep, addr, u16, size = _frames_arg(depth_frames)
+    poses = _f32(cam2base)
+    n = poses.size // 16
+    if size < n * d.im_width * d.im_height:
+        raise ValueError("depth_frames smaller than the pose list")
+    cost = np.zeros((int(dims[2]) + 7) // 8, np.uint64)
+    _check(load_library().tsdf_plan_z_cost(C.byref(d), n, addr, int(u16), poses.ctypes.data, int(frame_step),
+                                           cost.ctypes.data, cost.size), "tsdf_plan_z_cost")
+    return cost
+
+
+def split_slabs(cost, dim_z, n_slabs, base_cost=0.05):
+    """Equal-cost contiguous z-slabs cut at multiples of 8 planes (tsdf_split_slabs): list of (z_begin, z_end)."""
+    cost = np.ascontiguousarray(cost, dtype=np.uint64)
+    cuts = np.zeros(n_slabs + 1, np.int64)
+    _check(load_library().tsdf_split_slabs(cost.ctypes.data, cost.size, int(dim_z), int(n_slabs), float(base_cost),
+                                           cuts.ctypes.data), "tsdf_split_slabs")
+    return [(int(cuts[i]), int(cuts[i + 1])) for i in range(n_slabs)]
+
+
+def integrate_multi(volumes, depth_list, pose_list, n_frames=None):
+    """tsdf_integrate_multi: independent volumes of identical shape on one device, one launch."""
+    n_vols = len(volumes)
+    keeps, addrs, u16s, poses = [], [], [], []
+    for dep, pos in zip(depth_list, pose_list):
+        keep, addr, u16, _ = _frames_arg(dep)
+        keeps.append(keep); addrs.append(addr); u16s.append(u16)
+        poses.append(_f32(pos))
+    if len(set(u16s)) != 1:
+        raise ValueError("all volumes must get the same depth type")
+    n = poses[0].size // 16 if n_frames is None else int(n_frames)
+    vol_arr = (C.c_void_p * n_vols)(*[v._h for v in volumes])
+    frame_arr = (C.c_void_p * n_vols)(*addrs)
+    pose_arr = (C.c_void_p * n_vols)(*[p.ctypes.data for p in poses])
+    for v, k, p in zip(volumes, keeps, poses):
+        v._keepalive.append((k, p))
+    _check(volumes[0]._lib.tsdf_integrate_multi(vol_arr, n_vols, n, frame_arr, int(u16s[0]), pose_arr),
+           "tsdf_integrate_multi")
+
+
 def device_count() -> int:
     n = C.c_int32(0)
     _check(load_library().tsdf_device_count(C.byref(n)), "tsdf_device_count")
@@ -376,6 +451,13 @@ class Volume:
         p, n = C.c_void_p(), C.c_int64(0)
         _check(self._lib.tsdf_surface_device_ptr(self._h, C.byref(p), C.byref(n)), "tsdf_surface_device_ptr")
         return p.value, n.value
+
+    def z_cost(self) -> np.ndarray:
+        """Kept (tile, frame) pairs per group of 8 planes of this slab, accumulated by the fusion calls so far."""
+        nz = self.z_range[1] - self.z_range[0]
+        cost = np.zeros((nz + 7) // 8, np.uint64)
+        _check(self._lib.tsdf_get_z_cost(self._h, cost.ctypes.data, cost.size), "tsdf_get_z_cost")
+        return cost
 
     def stats(self) -> dict:
         s = Stats()

@@ -467,6 +467,8 @@ void stream_group_params(const tsdf_volume* v, int ng, tsdf::StreamLaunch* L) {
   *L = v->sl;
   L->n_frames = ng;
   L->n_chunks = (ng + L->chunk - 1) / L->chunk;
+  L->chunk = (ng + L->n_chunks - 1) / L->n_chunks;   // chunks of equal length (50 frames: 25 + 25, not 32 + 18)
+  L->n_chunks = (ng + L->chunk - 1) / L->chunk;
   L->cull_level = v->cull;
 }
 

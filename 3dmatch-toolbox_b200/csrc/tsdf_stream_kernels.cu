@@ -90,11 +90,16 @@ __global__ void __launch_bounds__(256) stream_mask_kernel(const __grid_constant_
   const int x_lo = (xt << L.lx_shift) * VEC, x_hi = min(L.dim_x - 1, x_lo + ((VEC << L.lx_shift) - 1));
   const int yb_lo = yb * rows_per_block, yb_hi = min(L.dim_y - 1, yb_lo + rows_per_block - 1);
   const int z_lo = J.z_begin + zg * ZT, z_hi = z_lo + ZT - 1;
-  unsigned prev_plus1 = 0u;
+  // Lanes span FRAMES: a lane block covers per_blk = chunk * floor(32 / chunk) consecutive frames, i.e. a whole number
+  // of chunks, so the ballots of one round hold the masks of up to 32 chunks (chunk = 1) and lane ci then finishes
+  // chunk ci of the block (mask words, item append) in parallel with the other lanes.
+  const int chunks_per_blk = 32 / L.chunk, per_blk = chunks_per_blk * L.chunk;
+  const unsigned sel = (L.chunk >= 32) ? 0xffffffffu : ((1u << L.chunk) - 1u);
+  unsigned carry_prev = 0u;  // (last non-empty chunk of this tile so far) + 1; warp-uniform
   unsigned long long cost = 0ull;
-  for (int c = 0; c < L.n_chunks; ++c) {
-    const int f = c * L.chunk + lane;
-    const bool valid = lane < L.chunk && f < L.n_frames;
+  for (int fb = 0; fb < L.n_frames; fb += per_blk) {
+    const int f = fb + lane;
+    const bool valid = lane < per_blk && f < L.n_frames;
     unsigned keep_w[kWarps], in_w[kWarps];
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) keep_w[w] = in_w[w] = 0u;
@@ -123,24 +128,31 @@ __global__ void __launch_bounds__(256) stream_mask_kernel(const __grid_constant_
         }
       }
     }
-    unsigned uni = 0u;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      uni |= keep_w[w];
-      cost += (unsigned)__popc(keep_w[w]);
-    }
+    for (int w = 0; w < kWarps; ++w) cost += (unsigned)__popc(keep_w[w]);
     if constexpr (!kCostOnly) {
-      uint2* out = J.masks + ((int64_t)c * L.n_btiles + btile) * kWarps;
+      // lane ci: chunk c = first chunk of the block + ci
+      const int c0 = fb / L.chunk, c = c0 + lane;
+      const bool mine = lane < chunks_per_blk && c < L.n_chunks;
+      const int sh = (lane < chunks_per_blk) ? lane * L.chunk : 0;
+      unsigned uni = 0u;
+      if (mine) {
+        uint2* out = J.masks + ((int64_t)c * L.n_btiles + btile) * kWarps;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w)
-        if (lane == w) out[w] = make_uint2(keep_w[w], in_w[w]);
-      if (uni != 0u) {
-        if (lane == 0) {
-          const unsigned pos = atomicAdd(&J.item_count[c], 1u);
-          J.items[(int64_t)c * L.n_btiles + pos] = (unsigned long long)(unsigned)btile | ((unsigned long long)prev_plus1 << 32);
+        for (int w = 0; w < kWarps; ++w) {
+          const unsigned kw = (keep_w[w] >> sh) & sel;
+          uni |= kw;
+          out[w] = make_uint2(kw, (in_w[w] >> sh) & sel);
         }
-        prev_plus1 = (unsigned)c + 1u;
       }
+      const unsigned nonempty = __ballot_sync(0xffffffffu, mine && uni != 0u);
+      if (mine && uni != 0u) {
+        const unsigned below = nonempty & ((1u << lane) - 1u);
+        const unsigned prev_plus1 = below ? (unsigned)(c0 + (31 - __clz(below)) + 1) : carry_prev;
+        const unsigned pos = atomicAdd(&J.item_count[c], 1u);
+        J.items[(int64_t)c * L.n_btiles + pos] = (unsigned long long)(unsigned)btile | ((unsigned long long)prev_plus1 << 32);
+      }
+      if (nonempty != 0u) carry_prev = (unsigned)(c0 + (31 - __clz(nonempty)) + 1);
     }
   }
   if (lane == 0 && J.zcost != nullptr && cost != 0ull) atomicAdd(&J.zcost[zg], cost);

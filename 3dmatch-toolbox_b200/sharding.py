@@ -158,20 +158,56 @@ def gather_surface(points: torch.Tensor, dst: int = 0):
     return torch.cat([bufs[r][: counts[r]] for r in range(world)], dim=0)
 
 
-def gather_slabs(slab: torch.Tensor, dim_z: int, dst: int = 0):
-    """Slab arrays [nz_r, dy, dx] -> the full [dim_z, dy, dx] volume on `dst` (for tsdf.bin)."""
+def gather_slabs(slab: torch.Tensor, dim_z: int, dst: int = 0, ranges=None):
+    """Slab arrays [nz_r, dy, dx] -> the full [dim_z, dy, dx] volume on `dst` (for tsdf.bin).
+
+    `ranges`: the (z_begin, z_end) of every rank (equal-cost slabs have different heights); None = the equal-height
+    partition of slab_range().  The heights are cross-checked against what the ranks actually hold."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return slab
     world, rank = dist.get_world_size(), dist.get_rank()
-    nz_max = max(slab_range(dim_z, r, world)[1] - slab_range(dim_z, r, world)[0] for r in range(world))
+    if ranges is None:
+        ranges = [slab_range(dim_z, r, world) for r in range(world)]
+    ranges = [(int(a), int(b)) for a, b in ranges]
+    if len(ranges) != world or ranges[0][0] != 0 or ranges[-1][1] != dim_z or any(a[1] != b[0] for a, b in zip(ranges, ranges[1:])):
+        raise ValueError(f"slab ranges {ranges} do not tile [0, {dim_z})")
+    n = torch.tensor([slab.shape[0]], dtype=torch.int64, device=slab.device)
+    heights = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(heights, n)
+    heights = [int(h.item()) for h in heights]
+    if heights != [b - a for a, b in ranges]:
+        raise ValueError(f"ranks hold slabs of {heights} planes, the ranges say {[b - a for a, b in ranges]}")
+    nz_max = max(heights)
     padded = torch.zeros((nz_max,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
     padded[: slab.shape[0]] = slab
     bufs = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(bufs, padded)
     if rank != dst:
         return None
-    parts = []
-    for r in range(world):
-        z0, z1 = slab_range(dim_z, r, world)
-        parts.append(bufs[r][: z1 - z0])
-    return torch.cat(parts, dim=0)
+    return torch.cat([bufs[r][: heights[r]] for r in range(world)], dim=0)
+
+
+# ---- equal-work slabs from the engine's own cull statistics (tsdf_plan_z_cost / tsdf_split_slabs) ----------------
+
+def split_groups(group_cost, dim_z: int, world: int, base_cost: float = 0.05):
+    """Contiguous z-slabs of (nearly) equal summed cost, cut at multiples of 8 planes.  `group_cost`: one value per
+    group of 8 planes (any non-negative floats; scaled to integers for the C routine)."""
+    from . import binding
+    c = np.maximum(np.asarray(group_cost, dtype=np.float64), 0.0)
+    scale = (2.0 ** 40) / max(float(c.max()), 1e-300)
+    return binding.split_slabs(np.round(c * scale).astype(np.uint64), dim_z, world, base_cost)
+
+
+def refine_group_cost(group_cost, ranges, rank_ms, base_cost: float = 0.05, damping: float = 0.8) -> np.ndarray:
+    """Feedback balancing at group (8-plane) granularity: scale the cost model by measured / modelled time of every
+    slab, interpolated between slab centres.  The model includes the same base cost per group as split_groups()."""
+    cost = np.asarray(group_cost, dtype=np.float64)
+    eff = cost + base_cost * cost.mean()
+    g_ranges = [(a // 8, -(-b // 8)) for a, b in ranges]
+    model = np.array([eff[a:b].sum() for a, b in g_ranges])
+    ratio = np.asarray(rank_ms, dtype=np.float64) / np.maximum(model, 1e-300)
+    ratio = (ratio / ratio.mean()) ** damping
+    centers = np.array([0.5 * (a + b - 1) for a, b in g_ranges])
+    scale = np.interp(np.arange(len(cost)), centers, ratio)
+    # scale the effective cost, then take the base part out again so that split_groups() adds it back unchanged
+    return np.maximum(eff * scale - base_cost * cost.mean(), 0.0)

@@ -1,5 +1,6 @@
-"""Diagnostic: time each of the N cost-balanced z-slabs of the 1024^3 workload on ONE GPU, one after the
-other, and compare the sum with the monolithic volume (isolates sharding overhead from multi-GPU effects)."""
+"""Diagnostic: time each of the N equal-work z-slabs of the 1024^3 workload on ONE GPU, one after the other, and
+compare the sum with the monolithic volume (isolates sharding overhead from multi-GPU effects).
+    python scripts/slab_overhead.py [frames] [n_slabs] [K ...]"""
 import sys
 from pathlib import Path
 
@@ -18,25 +19,29 @@ cfg = dict(synth.CONFIGS["1024"], frames=F)
 grid = cfg["grid"]
 device = torch.device("cuda", 0)
 depth, poses = bench.build_inputs(pkg, cfg, device, 0, 1, None)
-cost = pkg.sharding.estimate_plane_cost(grid.dims, grid.origin, grid.voxel_size, synth.CAM_K, poses)
+cost = pkg.plan_z_cost(grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin, synth.CAM_K, depth, poses,
+                       frame_step=max(1, F // 128)).astype(np.float64)
 
 
-def time_slab(z0, z1, batch, tuning=0):
+def time_slab(z0, z1, batch):
     with pkg.Volume(grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin, synth.CAM_K, z_range=(z0, z1),
-                    max_batch=batch, tuning=tuning) as vol:
+                    max_batch=batch) as vol:
         vol.integrate_batch(depth, poses)
-        vol.reset()
-        vol.synchronize()
-        vol.timer_start()
-        vol.integrate_batch(depth, poses)
-        return vol.timer_stop()
+        ts = []
+        for _ in range(2):
+            vol.reset()
+            vol.synchronize()
+            vol.timer_start()
+            vol.integrate_batch(depth, poses)
+            ts.append(vol.timer_stop())
+        return min(ts)
 
 
-CASES = [tuple(int(v, 0) for v in a.split(':')) for a in sys.argv[3:]] or [(16, 1 << 10), (16, 0), (16, 3 << 10), (32, 0)]
-for batch, tuning in CASES:
-    whole = time_slab(0, grid.dims[2], batch, tuning)
-    parts = [time_slab(a, b, batch, tuning) for a, b in pkg.sharding.weighted_slab_ranges(cost, N)]
-    print(f"K={batch} tuning={tuning}: whole {whole:.1f} ms, {N} slabs sum {sum(parts):.1f} ms (+{100 * (sum(parts) / whole - 1):.1f} %), "
-          f"max {max(parts):.1f} -> speed-up {whole / max(parts):.2f}x; parts {[round(p, 1) for p in parts]}")
-
-
+for batch in [int(a) for a in sys.argv[3:]] or [32]:
+    whole = time_slab(0, grid.dims[2], batch)
+    for base in (0.05, 0.15):
+        ranges = pkg.sharding.split_groups(cost, grid.dims[2], N, base)
+        parts = [time_slab(a, b, batch) for a, b in ranges]
+        print(f"K={batch} base_cost={base}: whole {whole:.1f} ms, {N} slabs sum {sum(parts):.1f} ms (+{100 * (sum(parts) / whole - 1):.1f} %), "
+              f"max {max(parts):.1f} (mean {sum(parts) / N:.1f}) -> speed-up {whole / max(parts):.2f}x, "
+              f"{whole / (sum(parts) / N):.2f}x at perfect balance; cuts {[a for a, _ in ranges]} parts {[round(p, 1) for p in parts]}", flush=True)

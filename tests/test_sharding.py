@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, weighted):
     import sys
     sys.path.insert(0, str(ROOT))
     import __graft_entry__ as graft
@@ -41,11 +41,13 @@ def _worker(rank, world, port, out_dir):
         depth = oracle.depth_from_u16(mm.numpy().astype(np.uint16))
         c2w, b2w = synth.make_poses(frames)
         poses = np.stack([oracle.cam2base_from_world(b2w, m).ravel() for m in c2w])
-        z0, z1 = sharding.slab_range(dims[2], rank, world)
+        # equal-cost slabs have different heights: the gather must follow the actual ranges
+        ranges = sharding.weighted_slab_ranges(np.linspace(1.0, 6.0, dims[2]), world) if weighted else None
+        z0, z1 = ranges[rank] if weighted else sharding.slab_range(dims[2], rank, world)
         t, w = oracle.fuse(K, poses, depth, dims, origin, voxel, trunc, z_range=(z0, z1))
         pts = oracle.extract_surface(t, w, dims, origin, voxel, z_range=(z0, z1))
         cloud = sharding.gather_surface(torch.from_numpy(pts), dst=0)
-        full_t = sharding.gather_slabs(torch.from_numpy(t), dims[2], dst=0)
+        full_t = sharding.gather_slabs(torch.from_numpy(t), dims[2], dst=0, ranges=ranges)
         if rank == 0:
             t_ref, w_ref = oracle.fuse(K, poses, depth, dims, origin, voxel, trunc)
             pts_ref = oracle.extract_surface(t_ref, w_ref, dims, origin, voxel)
@@ -59,10 +61,36 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_fusion_equals_monolithic_gloo(world, tmp_path, oracle):
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("world,weighted", [(2, False), (3, False), (3, True)])
+def test_sharded_fusion_equals_monolithic_gloo(world, weighted, tmp_path, oracle):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), weighted), nprocs=world, join=True)
     assert (tmp_path / "result.txt").read_text() == "ok"
+
+
+def test_split_slabs_equal_cost_at_group_granularity(pkg):
+    """tsdf_split_slabs (host routine of the C ABI): contiguous, cut at multiples of 8 planes, every slab non-empty,
+    costs balanced as well as the granularity allows; refine_group_cost moves the cuts towards the slow rank."""
+    sh = pkg.sharding
+    rng = np.random.default_rng(3)
+    for dim_z, world in [(1024, 8), (1024, 3), (500, 4), (2048, 8), (64, 8), (300, 2), (8, 1)]:
+        n_groups = (dim_z + 7) // 8
+        cost = np.concatenate([np.linspace(1, 40, n_groups - n_groups // 4), np.full(n_groups // 4, 0.2)]) * 1e6
+        cost *= 1 + 0.05 * rng.standard_normal(n_groups)
+        ranges = sh.split_groups(cost, dim_z, world, base_cost=0.05)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == dim_z
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:])) and all(b > a for a, b in ranges)
+        assert all(a % 8 == 0 for a, _ in ranges)
+        eff = cost + 0.05 * cost.mean()
+        sums = np.array([eff[a // 8:-(-b // 8)].sum() for a, b in ranges])
+        if n_groups >= 16 * world:
+            assert sums.max() / sums.mean() < 1.0 + 2.5 * eff.max() / sums.mean(), (dim_z, world, sums)
+    ranges = sh.split_groups(np.ones(128), 1024, 4)
+    assert ranges == [(0, 256), (256, 512), (512, 768), (768, 1024)]
+    slow_last = sh.refine_group_cost(np.ones(128), ranges, [10.0, 10.0, 10.0, 16.0])
+    new = sh.split_groups(slow_last, 1024, 4)
+    assert new[-1][0] > ranges[-1][0]          # the slow last rank gets a shorter slab
+    with pytest.raises(pkg.TsdfError):
+        pkg.binding.split_slabs(np.ones(4, np.uint64), 32, 5)   # more slabs than groups
 
 
 def test_slab_ranges_tile_the_volume(pkg):

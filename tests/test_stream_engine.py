@@ -137,3 +137,81 @@ def test_misaligned_external_slab_is_rejected(pkg, synth):
 def test_shipped_library_rejects_reserved0(pkg, synth):
     with pytest.raises(pkg.TsdfError, match="reserved0"):
         pkg.Volume((64, 64, 64), ORIGIN, 0.05, 0.25, synth.CAM_K, tuning=5, validation=False)
+
+
+def test_integrate_multi_equals_separate_calls(pkg, oracle, sequence):
+    """tsdf_integrate_multi (BASELINE config 5: independent fragment volumes, one launch) == one tsdf_integrate_batch
+    per volume == the oracle; device, pinned and pageable uint16 inputs; also the fallback for differing volumes."""
+    import torch
+    n_frag, n_frames = 5, 40
+    dims, voxel, trunc = (120, 100, 76), 0.025, 0.125
+    data = []
+    for i in range(n_frag):
+        frames = list(range(50 * i, 50 * i + n_frames))
+        depth, mm, poses, K = sequence(frames, base_frame=50 * i)
+        data.append((depth, mm, poses, K))
+    K = data[0][3]
+    refs = [oracle.fuse(K, d[2], d[0], dims, ORIGIN, voxel, trunc) for d in data[:2]]
+    base = []
+    for depth, mm, poses, _ in data:
+        with pkg.Volume(dims, ORIGIN, voxel, trunc, K) as vol:
+            vol.integrate_batch(mm, poses)
+            t, w = vol.download()
+            base.append((t, w, vol.extract_surface()))
+    for (t, w, _), (t_ref, w_ref) in zip(base, refs):
+        assert_bit_equal(w, w_ref, "separate weights vs oracle")
+        assert_bit_equal(t, t_ref, "separate tsdf vs oracle")
+    sources = {
+        "u16 device": [torch.from_numpy(d[1].view(np.int16)).cuda() for d in data],
+        "u16 pinned": [torch.from_numpy(d[1].view(np.int16)).pin_memory() for d in data],
+        "u16 pageable": [d[1] for d in data],
+        "float device": [torch.from_numpy(d[0]).cuda() for d in data],
+    }
+    for name, src in sources.items():
+        vols = [pkg.Volume(dims, ORIGIN, voxel, trunc, K) for _ in range(n_frag)]
+        for rep in range(2):   # twice: the second launch reuses every buffer
+            for v in vols:
+                v.reset()
+            pkg.integrate_multi(vols, src, [d[2] for d in data])
+        for v, (t_b, w_b, p_b) in zip(vols, base):
+            t, w = v.download()
+            assert_bit_equal(w, w_b, f"multi weights [{name}]")
+            assert_bit_equal(t, t_b, f"multi tsdf [{name}]")
+            assert_bit_equal(v.extract_surface(), p_b, f"multi points [{name}]")
+            v.close()
+    # volumes of different shape: the call falls back to one launch per volume
+    v_a = pkg.Volume(dims, ORIGIN, voxel, trunc, K)
+    v_b = pkg.Volume((dims[0], dims[1], dims[2] - 12), ORIGIN, voxel, trunc, K)
+    pkg.integrate_multi([v_a, v_b], [data[0][1], data[1][1]], [data[0][2], data[1][2]])
+    t, w = v_a.download()
+    assert_bit_equal(t, base[0][0], "fallback tsdf")
+    t, w = v_b.download()
+    assert_bit_equal(t, base[1][0][: dims[2] - 12], "fallback tsdf (shorter volume)")
+    v_a.close(); v_b.close()
+
+
+def test_plan_z_cost_matches_engine_statistics_and_balances(pkg, sequence):
+    """tsdf_plan_z_cost (whole grid, no volume memory) == the counts the fusion kernel's mask pre-pass accumulates
+    (tsdf_get_z_cost), is deterministic, and its equal-cost cuts are far better balanced than equal heights."""
+    import torch
+    frames = list(range(0, 128, 2))
+    depth, mm, poses, K = sequence(frames)
+    dims, voxel = (256, 256, 256), 0.012
+    trunc = float(np.float32(voxel) * np.float32(5))
+    cost = pkg.plan_z_cost(dims, ORIGIN, voxel, trunc, K, depth, poses)
+    cost_dev = pkg.plan_z_cost(dims, ORIGIN, voxel, trunc, K, torch.from_numpy(mm.view(np.int16)).cuda(), poses)
+    assert cost.shape == (32,) and cost.sum() > 0 and np.array_equal(cost, cost_dev)
+    with pkg.Volume(dims, ORIGIN, voxel, trunc, K) as vol:
+        vol.integrate_batch(depth, poses)
+        assert np.array_equal(vol.z_cost(), cost)
+    ranges = pkg.sharding.split_groups(cost, dims[2], 4)
+    part = []
+    for a, b in ranges:
+        with pkg.Volume(dims, ORIGIN, voxel, trunc, K, z_range=(a, b)) as vol:
+            vol.integrate_batch(depth, poses)
+            part.append(int(vol.z_cost().sum()))
+    assert sum(part) == int(cost.sum())           # slabs cut at multiples of 8 planes see exactly the same tiles
+    eq = [int(cost[a // 8:b // 8].sum()) for a, b in [(0, 64), (64, 128), (128, 192), (192, 256)]]
+    assert max(part) / (sum(part) / 4) < max(eq) / (sum(eq) / 4)
+    sub = pkg.plan_z_cost(dims, ORIGIN, voxel, trunc, K, depth, poses, frame_step=4)
+    assert 0.15 * cost.sum() < sub.sum() < 0.4 * cost.sum()
