@@ -30,6 +30,9 @@ EXPORTED_SYMBOLS = [
     "tsdf_invert_matrix", "tsdf_Integrate", "tsdf_SaveVoxelGrid2SurfacePointCloud", "tsdf_last_error",
     "tsdf_version", "tsdf_device_count", "tsdf_selftest_rounding", "tsdf_ComputeTDF", "tsdf_tdf_grid_from_points",
     "tsdf_point_cloud_to_tdf", "tsdf_integrate_multi", "tsdf_plan_z_cost", "tsdf_get_z_cost", "tsdf_split_slabs",
+    "tsdf_sharded_create", "tsdf_sharded_destroy", "tsdf_sharded_reset", "tsdf_sharded_synchronize",
+    "tsdf_sharded_integrate_batch", "tsdf_sharded_extract_surface", "tsdf_sharded_copy_surface", "tsdf_sharded_write_bin",
+    "tsdf_sharded_slab",
 ]
 
 
@@ -105,6 +108,13 @@ def load_library(validation: bool = False) -> C.CDLL:
         "tsdf_plan_z_cost": [C.POINTER(VolumeDesc), C.c_int32, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32],
         "tsdf_get_z_cost": [vp, vp, C.c_int32],
         "tsdf_split_slabs": [vp, C.c_int32, C.c_int64, C.c_int32, C.c_double, vp],
+        "tsdf_sharded_create": [C.POINTER(VolumeDesc), C.c_int32, vp, vp, C.POINTER(vp)],
+        "tsdf_sharded_reset": [vp], "tsdf_sharded_synchronize": [vp],
+        "tsdf_sharded_integrate_batch": [vp, C.c_int32, vp, C.c_int32, vp],
+        "tsdf_sharded_extract_surface": [vp, C.c_float, C.c_float, i64p],
+        "tsdf_sharded_copy_surface": [vp, vp, C.c_int64],
+        "tsdf_sharded_write_bin": [vp, C.c_char_p],
+        "tsdf_sharded_slab": [vp, C.c_int32, C.POINTER(vp), i64p, i64p, C.POINTER(C.c_int32)],
         "tsdf_device_count": [C.POINTER(C.c_int32)],
         "tsdf_selftest_rounding": [C.c_int32, i64p],
     }
@@ -114,6 +124,8 @@ def load_library(validation: bool = False) -> C.CDLL:
         fn.restype = C.c_int
     lib.tsdf_destroy.argtypes = [vp]
     lib.tsdf_destroy.restype = None
+    lib.tsdf_sharded_destroy.argtypes = [vp]
+    lib.tsdf_sharded_destroy.restype = None
     lib.tsdf_multiply_matrix.argtypes = [vp, vp, vp]
     lib.tsdf_multiply_matrix.restype = None
     lib.tsdf_depth_from_u16.argtypes = [vp, C.c_int64, vp]
@@ -474,3 +486,73 @@ class Volume:
         ms = C.c_float(0)
         _check(self._lib.tsdf_timer_stop(self._h, C.byref(ms)), "tsdf_timer_stop")
         return ms.value
+
+
+class ShardedVolume:
+    """One volume cut into z-slabs over several GPUs, driven from one process (tsdf_sharded_*): frames are uploaded
+    once and broadcast with NCCL, slabs fuse independently, points are gathered in z order to the first device."""
+
+    def __init__(self, dims, origin, voxel_size, trunc_margin, cam_K, n_slabs, devices=None, z_cuts=None,
+                 im_size=(640, 480), max_batch=0, cull_level=-1):
+        self._lib = load_library()
+        d = make_desc(dims, origin, voxel_size, trunc_margin, cam_K, im_size, max_batch=max_batch, cull_level=cull_level)
+        dev = np.ascontiguousarray(devices, dtype=np.int32) if devices is not None else None
+        cuts = np.ascontiguousarray(z_cuts, dtype=np.int64) if z_cuts is not None else None
+        if dev is not None and dev.size != n_slabs:
+            raise ValueError("one device per slab")
+        if cuts is not None and cuts.size != n_slabs + 1:
+            raise ValueError("n_slabs + 1 cuts")
+        self._h = C.c_void_p()
+        _check(self._lib.tsdf_sharded_create(C.byref(d), n_slabs, dev.ctypes.data if dev is not None else None,
+                                             cuts.ctypes.data if cuts is not None else None, C.byref(self._h)),
+               "tsdf_sharded_create")
+        self.dims, self.n_slabs = tuple(int(v) for v in dims), n_slabs
+        self._keepalive = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tsdf_sharded_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def slabs(self):
+        out = []
+        for i in range(self.n_slabs):
+            a, b, dv = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+            _check(self._lib.tsdf_sharded_slab(self._h, i, None, C.byref(a), C.byref(b), C.byref(dv)), "tsdf_sharded_slab")
+            out.append((a.value, b.value, dv.value))
+        return out
+
+    def reset(self):
+        _check(self._lib.tsdf_sharded_reset(self._h), "tsdf_sharded_reset")
+
+    def synchronize(self):
+        _check(self._lib.tsdf_sharded_synchronize(self._h), "tsdf_sharded_synchronize")
+        self._keepalive.clear()
+
+    def integrate_batch(self, depth_frames, cam2base, n_frames=None):
+        keep, addr, u16, _ = _frames_arg(depth_frames)
+        poses = _f32(cam2base)
+        n = poses.size // 16 if n_frames is None else int(n_frames)
+        self._keepalive.append((keep, poses))
+        _check(self._lib.tsdf_sharded_integrate_batch(self._h, n, addr, int(u16), poses.ctypes.data),
+               "tsdf_sharded_integrate_batch")
+
+    def extract_surface(self, tsdf_thresh=0.2, weight_thresh=1.0) -> np.ndarray:
+        n = C.c_int64(0)
+        _check(self._lib.tsdf_sharded_extract_surface(self._h, tsdf_thresh, weight_thresh, C.byref(n)),
+               "tsdf_sharded_extract_surface")
+        out = np.empty((n.value, 3), np.float32)
+        _check(self._lib.tsdf_sharded_copy_surface(self._h, out.ctypes.data, n.value), "tsdf_sharded_copy_surface")
+        self._keepalive.clear()
+        return out
+
+    def write_bin(self, path):
+        _check(self._lib.tsdf_sharded_write_bin(self._h, os.fsencode(path)), "tsdf_sharded_write_bin")

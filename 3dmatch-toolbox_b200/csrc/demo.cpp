@@ -15,19 +15,25 @@
 //   --image W H              depth image size (reference: 640 480, demo.cu:87-88)
 //   --bin [path]             also write the TSDF volume as tsdf.bin (demo.cu:196-213)
 //   --ply path               surface point cloud path (default tsdf.ply)
-//   --batch K                frames fused per pass over the volume (default 8)
+//   --batch K                frames per pass over the volume (default 32)
 //   --device N               CUDA device ordinal (default 0)
+//   --gpus N                 cut the volume into N z-slabs of equal work over devices 0 .. N-1 (frames broadcast with
+//                            NCCL, slabs gathered only for output; tsdf.ply / tsdf.bin are byte-identical to --gpus 1)
+//   --threads T              PNG decoder threads (default: hardware concurrency, at most 16)
 //   --thresh T W             surface thresholds (reference: 0.2 1.0, demo.cu:194)
 //
 // All computation runs on the GPU through the C ABI (include/tsdf_fusion.h); host code here only
 // reads files and does the 4x4 pose algebra with the reference's rounding.
 #include "tsdf_fusion.h"
 
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -68,7 +74,7 @@ int main(int argc, char* argv[]) {
   long long dim_x = 500, dim_y = 500, dim_z = 500;
   // extensions
   std::string ply_path = "tsdf.ply", bin_path;
-  int batch = 8, device = 0;
+  int batch = 32, device = 0, gpus = 1, threads = 0;
   float tsdf_thresh = 0.2f, weight_thresh = 1.0f;  // demo.cu:194
 
   int next = 1;
@@ -98,11 +104,20 @@ int main(int argc, char* argv[]) {
     else if (a == "--ply") { need(1); ply_path = argv[++i]; }
     else if (a == "--batch") { need(1); batch = atoi(argv[++i]); }
     else if (a == "--device") { need(1); device = atoi(argv[++i]); }
+    else if (a == "--gpus") { need(1); gpus = atoi(argv[++i]); }
+    else if (a == "--threads") { need(1); threads = atoi(argv[++i]); }
     else if (a == "--thresh") { need(2); tsdf_thresh = atof(argv[i + 1]); weight_thresh = atof(argv[i + 2]); i += 2; }
     else fatal("unknown option " + a);
   }
   if (batch < 1) batch = 1;
   if (batch > TSDF_MAX_BATCH) batch = TSDF_MAX_BATCH;
+  if (gpus < 1) gpus = 1;
+  if (threads < 1) {
+    threads = (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 4;
+    if (threads > 16) threads = 16;
+  }
+  const int n_frames = (int)num_frames > 0 ? (int)num_frames : 0;
 
   // demo.cu:116-117 -- camera intrinsics
   float cam_K[9];
@@ -114,7 +129,6 @@ int main(int argc, char* argv[]) {
         "LoadMatrixFromFile(base pose)");
   tsdf_invert_matrix(base2world, base2world_inv);
 
-  // demo.cu:131-153 -- volume initialised directly in HBM
   tsdf_volume_desc desc;
   memset(&desc, 0, sizeof desc);
   desc.dim_x = dim_x; desc.dim_y = dim_y; desc.dim_z = dim_z;
@@ -125,51 +139,107 @@ int main(int argc, char* argv[]) {
   desc.device = device;
   desc.max_batch = batch;
   desc.cull_level = -1;
-  tsdf_volume* vol = nullptr;
-  check(tsdf_create(&desc, &vol), "tsdf_create");
 
-  // demo.cu:156-183 -- frame loop; frames are handed to the engine `batch` at a time
+  // demo.cu:156-171 -- the frames are decoded by a pool of threads (PNG inflate is the slowest host step) into one
+  // buffer that lives until the end of the run, so nothing has to wait for the GPU before it is reused; the main
+  // thread hands every completed group of frames to the engine, which fuses it asynchronously while the pool decodes
+  // the next ones
   const size_t px = (size_t)im_width * im_height;
-  std::vector<uint16_t> depth_mm(px * batch);
-  std::vector<float> poses(16 * (size_t)batch);
-  int pending = 0;
-  auto flush = [&]() {
-    if (pending == 0) return;
-    check(tsdf_integrate_batch_u16(vol, pending, depth_mm.data(), poses.data()), "Integrate");
-    check(tsdf_synchronize(vol), "Integrate");  // the staging vectors are reused
-    pending = 0;
-  };
-  for (int frame_idx = first_frame_idx; frame_idx < first_frame_idx + (int)num_frames; ++frame_idx) {
-    const std::string prefix = frame_prefix(data_path, frame_idx);
-    const std::string depth_im_file = prefix + ".depth.png";
-    if (tsdf_read_depth_png_u16(depth_im_file.c_str(), im_height, im_width, depth_mm.data() + px * pending) != TSDF_OK) {
-      std::cout << "Error: depth image file not read!" << std::endl;  // utils.hpp:77
-      fatal(tsdf_last_error());
+  std::vector<uint16_t> depth_mm(px * (size_t)n_frames);
+  std::vector<float> poses(16 * (size_t)n_frames);
+  std::vector<std::atomic<int>> done((size_t)n_frames);
+  for (auto& d : done) d.store(0);
+  std::vector<std::string> errors((size_t)n_frames);
+  std::atomic<int> next_frame{0};
+  auto decode = [&]() {
+    for (int i = next_frame++; i < n_frames; i = next_frame++) {
+      const std::string prefix = frame_prefix(data_path, first_frame_idx + i);
+      float cam2world[16];
+      if (tsdf_read_depth_png_u16((prefix + ".depth.png").c_str(), im_height, im_width, depth_mm.data() + px * (size_t)i) != TSDF_OK) {
+        errors[i] = std::string("Error: depth image file not read!\n") + tsdf_last_error();   // utils.hpp:77
+        done[i].store(2);
+        continue;
+      }
+      if (tsdf_load_matrix((prefix + ".pose.txt").c_str(), 4, 4, cam2world) != TSDF_OK) {
+        errors[i] = std::string("LoadMatrixFromFile(pose): ") + tsdf_last_error();
+        done[i].store(2);
+        continue;
+      }
+      tsdf_multiply_matrix(base2world_inv, cam2world, &poses[16 * (size_t)i]);  // demo.cu:171
+      done[i].store(1);
     }
-    float cam2world[16];
-    check(tsdf_load_matrix((prefix + ".pose.txt").c_str(), 4, 4, cam2world), "LoadMatrixFromFile(pose)");
-    tsdf_multiply_matrix(base2world_inv, cam2world, &poses[16 * (size_t)pending]);  // demo.cu:171
-    std::cout << "Fusing: " << depth_im_file << std::endl;                          // demo.cu:177
-    if (++pending == batch) flush();
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads && t < n_frames; ++t) pool.emplace_back(decode);
+  auto wait_frames = [&](int lo, int hi) {   // frames [lo, hi) decoded; prints the reference's progress lines in order
+    for (int i = lo; i < hi; ++i) {
+      while (done[i].load() == 0) std::this_thread::sleep_for(std::chrono::microseconds(200));
+      if (done[i].load() == 2) {
+        for (auto& t : pool) t.join();
+        if (errors[i].rfind("Error:", 0) == 0) {
+          std::cout << "Error: depth image file not read!" << std::endl;
+          fatal(errors[i].substr(errors[i].find('\n') + 1));
+        }
+        fatal(errors[i]);
+      }
+      std::cout << "Fusing: " << frame_prefix(data_path, first_frame_idx + i) << ".depth.png" << std::endl;  // demo.cu:177
+    }
+  };
+
+  tsdf_volume* vol = nullptr;
+  tsdf_sharded* shard = nullptr;
+  if (gpus == 1) {
+    // demo.cu:131-153 -- volume initialised directly in HBM
+    check(tsdf_create(&desc, &vol), "tsdf_create");
+    const int group = 128;
+    for (int f0 = 0; f0 < n_frames; f0 += group) {
+      const int n = (n_frames - f0 < group) ? n_frames - f0 : group;
+      wait_frames(f0, f0 + n);
+      check(tsdf_integrate_batch_u16(vol, n, depth_mm.data() + px * (size_t)f0, poses.data() + 16 * (size_t)f0), "Integrate");
+    }
+  } else {
+    // equal-work z-slabs need the whole trajectory: decode first, then plan, then fuse
+    wait_frames(0, n_frames);
+    const int n_groups = (int)((dim_z + 7) / 8);
+    std::vector<uint64_t> cost((size_t)n_groups, 1);
+    std::vector<int64_t> cuts((size_t)gpus + 1);
+    if (n_frames > 0)
+      check(tsdf_plan_z_cost(&desc, n_frames, depth_mm.data(), 1, poses.data(), n_frames > 128 ? n_frames / 128 : 1,
+                             cost.data(), n_groups), "tsdf_plan_z_cost");
+    check(tsdf_split_slabs(cost.data(), n_groups, dim_z, gpus, 0.05, cuts.data()), "tsdf_split_slabs");
+    check(tsdf_sharded_create(&desc, gpus, nullptr, cuts.data(), &shard), "tsdf_sharded_create");
+    check(tsdf_sharded_integrate_batch(shard, n_frames, depth_mm.data(), 1, poses.data()), "Integrate");
   }
-  flush();
+  for (auto& t : pool) t.join();
 
   // demo.cu:190-194
   std::cout << "Saving surface point cloud (" << ply_path << ")..." << std::endl;
   int64_t n_points = 0;
-  check(tsdf_extract_surface(vol, tsdf_thresh, weight_thresh, &n_points), "SaveVoxelGrid2SurfacePointCloud");
-  std::vector<float> xyz((size_t)n_points * 3);
-  check(tsdf_copy_surface(vol, xyz.data(), n_points), "SaveVoxelGrid2SurfacePointCloud");
+  std::vector<float> xyz;
+  if (vol) {
+    check(tsdf_extract_surface(vol, tsdf_thresh, weight_thresh, &n_points), "SaveVoxelGrid2SurfacePointCloud");
+    xyz.resize((size_t)n_points * 3);
+    check(tsdf_copy_surface(vol, xyz.data(), n_points), "SaveVoxelGrid2SurfacePointCloud");
+  } else {
+    check(tsdf_sharded_extract_surface(shard, tsdf_thresh, weight_thresh, &n_points), "SaveVoxelGrid2SurfacePointCloud");
+    xyz.resize((size_t)n_points * 3);
+    check(tsdf_sharded_copy_surface(shard, xyz.data(), n_points), "SaveVoxelGrid2SurfacePointCloud");
+  }
   check(tsdf_write_ply(ply_path.c_str(), xyz.data(), n_points), "SaveVoxelGrid2SurfacePointCloud");
 
   // demo.cu:196-213 (opt-in)
   if (!bin_path.empty()) {
     std::cout << "Saving TSDF voxel grid values to disk (" << bin_path << ")..." << std::endl;
-    std::vector<float> tsdf((size_t)dim_x * dim_y * dim_z);
-    check(tsdf_download(vol, tsdf.data(), nullptr), "tsdf_download");
-    check(tsdf_write_bin(bin_path.c_str(), dim_x, dim_y, dim_z, origin_x, origin_y, origin_z, voxel_size,
-                         trunc_margin, tsdf.data()), "tsdf_write_bin");
+    if (vol) {
+      std::vector<float> tsdf((size_t)dim_x * dim_y * dim_z);
+      check(tsdf_download(vol, tsdf.data(), nullptr), "tsdf_download");
+      check(tsdf_write_bin(bin_path.c_str(), dim_x, dim_y, dim_z, origin_x, origin_y, origin_z, voxel_size,
+                           trunc_margin, tsdf.data()), "tsdf_write_bin");
+    } else {
+      check(tsdf_sharded_write_bin(shard, bin_path.c_str()), "tsdf_write_bin");
+    }
   }
   tsdf_destroy(vol);
+  tsdf_sharded_destroy(shard);
   return 0;
 }

@@ -15,7 +15,10 @@
  *   depth-fusion/utils.hpp:74-86   ReadDepth                       -> tsdf_read_depth_png, tsdf_depth_from_u16
  *   depth-fusion/utils.hpp:89-109  multiply_matrix                 -> tsdf_multiply_matrix
  *   depth-fusion/utils.hpp:112-238 invert_matrix                   -> tsdf_invert_matrix
- *   depth-fusion/fuseSceneFragments.m:36-81 fragment loop          -> bin/fuse_fragments (built on this ABI)
+ *   depth-fusion/fuseSceneFragments.m:36-81 fragment loop          -> bin/fuse_fragments (built on this ABI),
+ *                                                                     tsdf_integrate_multi
+ *   (no counterpart: the reference is single-GPU)                  -> tsdf_sharded_* (z-slabs over the GPUs of a box),
+ *                                                                     tsdf_plan_z_cost, tsdf_split_slabs
  *   core/demo.cu:22-57,100-163     ComputeTDF + grid/occupancy     -> tsdf_ComputeTDF, tsdf_tdf_grid_from_points,
  *                                                                     tsdf_point_cloud_to_tdf   
  *
@@ -121,6 +124,33 @@ int tsdf_get_z_cost(tsdf_volume *v, uint64_t *cost, int32_t n_groups);
  * z_cuts[n_slabs] = dim_z.  base_cost: cost of a fully culled group relative to the mean group (0.05 is typical). */
 int tsdf_split_slabs(const uint64_t *cost, int32_t n_groups, int64_t dim_z, int32_t n_slabs, double base_cost,
                      int64_t *z_cuts);
+
+/* ---- one volume over several GPUs (extends demo.cu:72-216 to a multi-GPU box) -- */
+/* The grid of `desc` cut into n_slabs contiguous z-slabs, slab i resident on CUDA device devices[i] (NULL: devices
+ * 0 .. n_slabs-1; a device may hold several slabs).  z_cuts: n_slabs + 1 ascending plane indices from 0 to dim_z
+ * (NULL: equal heights; see tsdf_plan_z_cost / tsdf_split_slabs for equal-work cuts).  desc->device, z_begin/z_end,
+ * stream and ext_* are ignored.  One host thread drives all devices; NCCL (libnccl.so.2, loaded at run time) carries
+ * the frame broadcast and the surface gather between distinct devices. */
+typedef struct tsdf_sharded tsdf_sharded;
+int tsdf_sharded_create(const tsdf_volume_desc *desc, int32_t n_slabs, const int32_t *devices, const int64_t *z_cuts,
+                        tsdf_sharded **out);
+void tsdf_sharded_destroy(tsdf_sharded *s);
+int tsdf_sharded_reset(tsdf_sharded *s);
+int tsdf_sharded_synchronize(tsdf_sharded *s);
+/* n_frames reference launches in order (demo.cu:156-183) on every slab: the frames (float metres or, with
+ * frames_are_u16, raw uint16 millimetres; host memory or memory of devices[0]) are uploaded once, 128 at a time, and
+ * broadcast with ncclBroadcast while the previous 128 are being fused.  Asynchronous. */
+int tsdf_sharded_integrate_batch(tsdf_sharded *s, int32_t n_frames, const void *frames, int32_t frames_are_u16,
+                                 const float *cam2base);
+/* Per-slab extraction, then the ordered gather (ncclSend / ncclRecv) of the slab points to devices[0]: slab order is
+ * ascending z, i.e. ascending linear voxel index, so the gathered list is the reference's tsdf.ply payload. */
+int tsdf_sharded_extract_surface(tsdf_sharded *s, float tsdf_thresh, float weight_thresh, int64_t *n_points);
+int tsdf_sharded_copy_surface(tsdf_sharded *s, float *xyz_host, int64_t capacity_points);
+/* tsdf.bin (demo.cu:196-213) written slab by slab at each slab's byte offset; the volume never has to fit one host
+ * buffer. */
+int tsdf_sharded_write_bin(tsdf_sharded *s, const char *path);
+/* Slab i: its engine handle (owned by s), plane range and device.  Any output pointer may be NULL. */
+int tsdf_sharded_slab(tsdf_sharded *s, int32_t i, tsdf_volume **vol, int64_t *z_begin, int64_t *z_end, int32_t *device);
 
 /* ---- results --------------------------------------------------------------------------------- */
 /* Device->host copy of the slab (demo.cu:186-187).  Either pointer may be NULL. */

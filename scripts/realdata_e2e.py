@@ -1,0 +1,78 @@
+"""Real-data end to end (BASELINE config 1, the reference's own fixture): the reference's `demo` program built
+unchanged for sm_100a (oracle/_ref/demo_ref: its main, its per-frame cudaMemcpys, its kernel, its PLY writer; only the
+PNG decode is substituted) against bin/demo, both with the reference's default arguments (demo.cu:75-99) on the
+50-frame sample sequence staged under oracle/_ref/sample.  Wall time of the whole process, best of N; tsdf.ply compared.
+
+    python scripts/realdata_e2e.py [runs] > profiles/r02_realdata_e2e.json
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+SAMPLE = ROOT / "oracle" / "_ref" / "sample"
+REF = ROOT / "oracle" / "_ref" / "demo_ref"
+OURS = ROOT / "3dmatch-toolbox_b200" / "bin" / "demo"
+ARGS = [str(SAMPLE / "camera-intrinsics.txt"), str(SAMPLE / "rgbd-frames"), "8", "8", "50", "-1.5", "-1.5", "0.5", "0.006", "0.03"]
+
+
+def run(binary, extra, runs):
+    best, out = None, None
+    for _ in range(runs):
+        with tempfile.TemporaryDirectory() as tmp:
+            t0 = time.perf_counter()
+            r = subprocess.run([str(binary)] + ARGS + extra, cwd=tmp, capture_output=True, text=True, timeout=600)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return None, {"error": r.stderr[-400:]}
+            ply = (Path(tmp) / "tsdf.ply").read_bytes()
+            if best is None or dt < best:
+                best, out = dt, ply
+    return best, out
+
+
+def points(ply):
+    body = ply.split(b"end_header\n", 1)[1]
+    return np.frombuffer(body, dtype=np.float32).reshape(-1, 3)
+
+
+def main():
+    runs = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    if not (SAMPLE / ".staged").exists() or not REF.exists():
+        print(json.dumps({"unavailable": "oracle/_ref/demo_ref or oracle/_ref/sample missing (built by oracle/Makefile where /root/reference exists)"}))
+        return
+    t_ref, ply_ref = run(REF, [], runs)
+    t_ours, ply_ours = run(OURS, [], runs)
+    t_ours1, ply_ours1 = run(OURS, ["--threads", "1"], runs)
+    if t_ref is None or t_ours is None:
+        print(json.dumps({"error": {"reference": ply_ref if t_ref is None else "ok", "ours": ply_ours if t_ours is None else "ok"}}))
+        return
+    a, b = points(ply_ref), points(ply_ours)
+    sa = set(map(bytes, a.view(np.uint8).reshape(len(a), 12)))
+    sb = set(map(bytes, b.view(np.uint8).reshape(len(b), 12)))
+    out = {
+        "workload": "reference default arguments (demo.cu:75-99): 50 frames 640x480 of data/sample/depth-fusion-demo, 500^3 grid, 6 mm voxels, 3 cm truncation",
+        "voxel_updates": 500 ** 3 * 50,
+        "reference_binary": {"seconds": round(t_ref, 3), "what": "depth-fusion/demo.cu built unchanged for sm_100a (compile.sh:18 flags), PNG decode through the stand-in imread",
+                             "voxel_updates_per_sec": 500 ** 3 * 50 / t_ref},
+        "bin_demo": {"seconds": round(t_ours, 3), "voxel_updates_per_sec": 500 ** 3 * 50 / t_ours,
+                     "seconds_one_decoder_thread": round(t_ours1, 3) if t_ours1 else None},
+        "wall_time_ratio": round(t_ref / t_ours, 2),
+        "ply": {"reference_points": int(len(a)), "ours_points": int(len(b)), "byte_identical": ply_ref == ply_ours,
+                "points_only_in_reference": len(sa - sb), "points_only_in_ours": len(sb - sa),
+                "note": "the reference binary is the default --fmad=true build with the device powf: voxels on a rounding / "
+                        "threshold knife edge can differ (SURVEY.md 8a-notes 2); bin/demo is bit-exact against the "
+                        "--fmad=false evaluation (tests/test_cli.py)"},
+        "host_cpus": os.cpu_count(), "runs": runs,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -163,3 +163,30 @@ def test_fuse_fragments_matches_per_fragment_demo(pkg, oracle, synth, tmp_path):
         assert info[1] == "".join("%15.8e\t " % v for v in pose[0]).rstrip(" ")
         assert len(info) == 5
     assert len(np.frombuffer((out / "scene-a" / "cloud_bin_0.ply").read_bytes().split(b"end_header\n")[1], np.float32)) > 300
+
+
+def test_cli_default_arguments_against_the_reference_binary(tmp_path):
+    """BASELINE config 1 on the reference's own fixture: bin/demo and the reference's demo program built unchanged for
+    sm_100a (oracle/_ref/demo_ref, default --fmad=true build) with the reference's default arguments.  The clouds must
+    agree except for knife-edge voxels (five contracted multiply-adds + the device powf)."""
+    import subprocess as sp
+    sample = ROOT / "oracle" / "_ref" / "sample"
+    ref = ROOT / "oracle" / "_ref" / "demo_ref"
+    if not (sample / ".staged").exists() or not ref.exists():
+        pytest.skip("oracle/_ref/demo_ref / sample not built (needs /root/reference at build time)")
+    args = [str(sample / "camera-intrinsics.txt"), str(sample / "rgbd-frames"), "8", "8", "50", "-1.5", "-1.5", "0.5", "0.006", "0.03"]
+    clouds = {}
+    for name, binary in (("ref", ref), ("ours", DEMO)):
+        d = tmp_path / name
+        d.mkdir()
+        run = sp.run([str(binary)] + args, cwd=d, capture_output=True, text=True, timeout=600)
+        assert run.returncode == 0, run.stderr
+        lines = run.stdout.splitlines()
+        assert lines[0].startswith("Fusing: ") and lines[0].endswith("frame-000008.depth.png") and len(lines) == 51
+        body = (d / "tsdf.ply").read_bytes().split(b"end_header\n", 1)[1]
+        clouds[name] = np.frombuffer(body, dtype=np.float32).reshape(-1, 3)
+    a, b = clouds["ref"], clouds["ours"]
+    sa = set(map(bytes, a.view(np.uint8).reshape(len(a), 12)))
+    sb = set(map(bytes, b.view(np.uint8).reshape(len(b), 12)))
+    assert len(a) > 100000
+    assert len(sa ^ sb) <= 2e-3 * len(a), (len(a), len(b), len(sa - sb), len(sb - sa))
