@@ -20,6 +20,8 @@
 //   --gpus N                 cut the volume into N z-slabs of equal work over devices 0 .. N-1 (frames broadcast with
 //                            NCCL, slabs gathered only for output; tsdf.ply / tsdf.bin are byte-identical to --gpus 1)
 //   --threads T              PNG decoder threads (default: hardware concurrency, at most 16)
+//   --timing                 phase times (JSON, one line) on stderr: CUDA context + volume init, waiting for the decoder,
+//                            fusion tail, extraction, file output
 //   --thresh T W             surface thresholds (reference: 0.2 1.0, demo.cu:194)
 //
 // All computation runs on the GPU through the C ABI (include/tsdf_fusion.h); host code here only
@@ -75,6 +77,11 @@ int main(int argc, char* argv[]) {
   // extensions
   std::string ply_path = "tsdf.ply", bin_path;
   int batch = 32, device = 0, gpus = 1, threads = 0;
+  bool timing = false;
+  const auto t_start = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count();
+  };
   float tsdf_thresh = 0.2f, weight_thresh = 1.0f;  // demo.cu:194
 
   int next = 1;
@@ -106,6 +113,7 @@ int main(int argc, char* argv[]) {
     else if (a == "--device") { need(1); device = atoi(argv[++i]); }
     else if (a == "--gpus") { need(1); gpus = atoi(argv[++i]); }
     else if (a == "--threads") { need(1); threads = atoi(argv[++i]); }
+    else if (a == "--timing") timing = true;
     else if (a == "--thresh") { need(2); tsdf_thresh = atof(argv[i + 1]); weight_thresh = atof(argv[i + 2]); i += 2; }
     else fatal("unknown option " + a);
   }
@@ -188,18 +196,26 @@ int main(int argc, char* argv[]) {
 
   tsdf_volume* vol = nullptr;
   tsdf_sharded* shard = nullptr;
+  double t_init = 0, t_decode_wait = 0;
   if (gpus == 1) {
     // demo.cu:131-153 -- volume initialised directly in HBM
+    const auto t0 = std::chrono::steady_clock::now();
     check(tsdf_create(&desc, &vol), "tsdf_create");
-    const int group = 128;
+    t_init = since(t0);
+    const int group = 32;
     for (int f0 = 0; f0 < n_frames; f0 += group) {
       const int n = (n_frames - f0 < group) ? n_frames - f0 : group;
+      const auto tw = std::chrono::steady_clock::now();
       wait_frames(f0, f0 + n);
+      t_decode_wait += since(tw);
       check(tsdf_integrate_batch_u16(vol, n, depth_mm.data() + px * (size_t)f0, poses.data() + 16 * (size_t)f0), "Integrate");
     }
   } else {
     // equal-work z-slabs need the whole trajectory: decode first, then plan, then fuse
+    const auto tw = std::chrono::steady_clock::now();
     wait_frames(0, n_frames);
+    t_decode_wait = since(tw);
+    const auto t0 = std::chrono::steady_clock::now();
     const int n_groups = (int)((dim_z + 7) / 8);
     std::vector<uint64_t> cost((size_t)n_groups, 1);
     std::vector<int64_t> cuts((size_t)gpus + 1);
@@ -208,8 +224,12 @@ int main(int argc, char* argv[]) {
                              cost.data(), n_groups), "tsdf_plan_z_cost");
     check(tsdf_split_slabs(cost.data(), n_groups, dim_z, gpus, 0.05, cuts.data()), "tsdf_split_slabs");
     check(tsdf_sharded_create(&desc, gpus, nullptr, cuts.data(), &shard), "tsdf_sharded_create");
+    t_init = since(t0);
     check(tsdf_sharded_integrate_batch(shard, n_frames, depth_mm.data(), 1, poses.data()), "Integrate");
   }
+  const auto t_fuse0 = std::chrono::steady_clock::now();
+  if (timing) check(vol ? tsdf_synchronize(vol) : tsdf_sharded_synchronize(shard), "synchronize");
+  const double t_fuse_tail = since(t_fuse0);
   for (auto& t : pool) t.join();
 
   // demo.cu:190-194
@@ -225,6 +245,8 @@ int main(int argc, char* argv[]) {
     xyz.resize((size_t)n_points * 3);
     check(tsdf_sharded_copy_surface(shard, xyz.data(), n_points), "SaveVoxelGrid2SurfacePointCloud");
   }
+  const double t_extract = since(t_fuse0) - t_fuse_tail;
+  const auto t_w0 = std::chrono::steady_clock::now();
   check(tsdf_write_ply(ply_path.c_str(), xyz.data(), n_points), "SaveVoxelGrid2SurfacePointCloud");
 
   // demo.cu:196-213 (opt-in)
@@ -239,7 +261,12 @@ int main(int argc, char* argv[]) {
       check(tsdf_sharded_write_bin(shard, bin_path.c_str()), "tsdf_write_bin");
     }
   }
+  const double t_write = since(t_w0);
   tsdf_destroy(vol);
   tsdf_sharded_destroy(shard);
+  if (timing)
+    fprintf(stderr, "{\"frames\": %d, \"decoder_threads\": %d, \"gpus\": %d, \"init_s\": %.4f, \"decode_wait_s\": %.4f, "
+            "\"fusion_tail_s\": %.4f, \"extract_s\": %.4f, \"write_s\": %.4f, \"total_s\": %.4f}\n",
+            n_frames, threads, gpus, t_init, t_decode_wait, t_fuse_tail, t_extract, t_write, since(t_start));
   return 0;
 }

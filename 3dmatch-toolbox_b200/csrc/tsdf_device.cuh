@@ -426,6 +426,191 @@ __device__ __forceinline__ void voxel_classify_pair(f32x2_t sx2, f32x2_t sy2, f3
   }
 }
 
+#ifdef TSDF_VALIDATION
+// Diagnostic twin of voxel_classify_pair (validation library only): the depth gathers carry an L2 evict_last cache
+// hint (createpolicy.fractional.L2::evict_last), the per-access form of an L2-persisting access-policy window, for
+// the A/B measurement in profiles/ (BASELINE north_star (2)).  Identical arithmetic.
+template <bool INTERIOR>
+__device__ __forceinline__ void voxel_classify_pair_hint(f32x2_t sx2, f32x2_t sy2, f32x2_t sz2, float zx, float zy, float zz,
+                                                    const Intrinsics& K, float im_w_f, float half_w, float half_h,
+                                                    const void* depth_biased, float trunc_margin, unsigned pend_inc0,
+                                                    unsigned pend_inc1, unsigned exact_bit0, unsigned exact_bit1,
+                                                    unsigned& pend, unsigned& exact, unsigned long long policy) {
+  if constexpr (INTERIOR) {
+    asm("{\n\t"
+        ".reg .b64 bz, cxx, cyy, czz, rr, kk, ua, va, tu, tv, ru, rv, du, dv, fi, dd, ee, bm, bk;\n\t"
+        ".reg .f32 z0, z1, r0, r1, a0, a1, b0, b1, i0, i1, d0, d1, e0, e1, mg;\n\t"
+        ".reg .b32 n0, n1;\n\t"
+        ".reg .u64 ad0, ad1;\n\t"
+        ".reg .pred pc0, pc1, pf0, pf1, pb0, pb1;\n\t"
+        "mov.b64 bz, {%5, %5};\n\t"
+        "add.rn.f32x2 cxx, %2, bz;\n\t"
+        "mov.b64 bz, {%6, %6};\n\t"
+        "add.rn.f32x2 cyy, %3, bz;\n\t"
+        "mov.b64 bz, {%7, %7};\n\t"
+        "add.rn.f32x2 czz, %4, bz;\n\t"
+        "mov.b64 {z0, z1}, czz;\n\t"
+        "rcp.approx.ftz.f32 r0, z0;\n\t"
+        "rcp.approx.ftz.f32 r1, z1;\n\t"
+        "mov.b64 rr, {r0, r1};\n\t"
+        "mov.b64 bk, {%8, %8};\n\t"
+        "mul.rn.f32x2 kk, rr, bk;\n\t"
+        "mov.b64 bk, {%10, %10};\n\t"
+        "fma.rn.f32x2 ua, cxx, kk, bk;\n\t"
+        "mov.b64 bk, {%9, %9};\n\t"
+        "mul.rn.f32x2 kk, rr, bk;\n\t"
+        "mov.b64 bk, {%11, %11};\n\t"
+        "fma.rn.f32x2 va, cyy, kk, bk;\n\t"
+        "mov.f32 mg, 0f4B400000;\n\t"
+        "mov.b64 bm, {mg, mg};\n\t"
+        "add.rn.f32x2 tu, ua, bm;\n\t"
+        "add.rn.f32x2 tv, va, bm;\n\t"
+        "sub.rn.f32x2 ru, tu, bm;\n\t"
+        "sub.rn.f32x2 rv, tv, bm;\n\t"
+        "sub.rn.f32x2 du, ua, ru;\n\t"
+        "sub.rn.f32x2 dv, va, rv;\n\t"
+        "mov.b64 bk, {%14, %14};\n\t"
+        "fma.rn.f32x2 fi, rv, bk, tu;\n\t"
+        "mov.b64 {a0, a1}, du;\n\t"
+        "mov.b64 {b0, b1}, dv;\n\t"
+        "abs.f32 a0, a0;\n\t"
+        "abs.f32 a1, a1;\n\t"
+        "abs.f32 b0, b0;\n\t"
+        "abs.f32 b1, b1;\n\t"
+        "setp.lt.f32 pc0, a0, %12;\n\t"
+        "setp.lt.f32 pc1, a1, %12;\n\t"
+        "setp.lt.and.f32 pc0, b0, %13, pc0;\n\t"
+        "setp.lt.and.f32 pc1, b1, %13, pc1;\n\t"
+        "mov.b64 {i0, i1}, fi;\n\t"
+        "mov.b32 n0, i0;\n\t"
+        "mov.b32 n1, i1;\n\t"
+        "mad.wide.u32 ad0, n0, 4, %15;\n\t"
+        "mad.wide.u32 ad1, n1, 4, %15;\n\t"
+        "ld.global.nc.L2::cache_hint.f32 d0, [ad0], %21;\n\t"
+        "ld.global.nc.L2::cache_hint.f32 d1, [ad1], %21;\n\t"
+        "mov.b64 dd, {d0, d1};\n\t"
+        "sub.rn.f32x2 ee, dd, czz;\n\t"
+        "mov.b64 {e0, e1}, ee;\n\t"
+        "setp.ge.and.f32 pf0, e0, %16, pc0;\n\t"   // the gather is unconditional here: an uncertain pixel
+        "setp.ge.and.f32 pf1, e1, %16, pc1;\n\t"   // must not count (the exact path will)
+        "@pf0 add.u32 %0, %0, %17;\n\t"
+        "@pf1 add.u32 %0, %0, %18;\n\t"
+        "abs.f32 e0, e0;\n\t"
+        "abs.f32 e1, e1;\n\t"
+        "setp.lt.f32 pb0, e0, %16;\n\t"
+        "setp.lt.f32 pb1, e1, %16;\n\t"
+        "not.pred pc0, pc0;\n\t"
+        "not.pred pc1, pc1;\n\t"
+        "or.pred pb0, pb0, pc0;\n\t"
+        "or.pred pb1, pb1, pc1;\n\t"
+        "@pb0 or.b32 %1, %1, %19;\n\t"
+        "@pb1 or.b32 %1, %1, %20;\n\t"
+        "}"
+        : "+r"(pend), "+r"(exact)
+        : "l"(sx2), "l"(sy2), "l"(sz2), "f"(zx), "f"(zy), "f"(zz), "f"(K.fx), "f"(K.fy), "f"(K.cx), "f"(K.cy),
+          "f"(K.lim_x), "f"(K.lim_y), "f"(im_w_f), "l"(depth_biased), "f"(trunc_margin), "r"(pend_inc0),
+          "r"(pend_inc1), "r"(exact_bit0), "r"(exact_bit1), "l"(policy));
+  } else {
+    asm("{\n\t"
+        ".reg .b64 bz, cxx, cyy, czz, rr, kk, ua, va, tu, tv, ru, rv, du, dv, fi, dd, ee, bm, bk, qu, qv;\n\t"
+        ".reg .f32 z0, z1, r0, r1, a0, a1, b0, b1, i0, i1, d0, d1, e0, e1, mg, g0, g1, h0, h1;\n\t"
+        ".reg .b32 n0, n1;\n\t"
+        ".reg .u64 ad0, ad1;\n\t"
+        ".reg .pred pc0, pc1, pg0, pg1, pp0, pp1, pf0, pf1, pb0, pb1;\n\t"
+        "mov.b64 bz, {%5, %5};\n\t"
+        "add.rn.f32x2 cxx, %2, bz;\n\t"
+        "mov.b64 bz, {%6, %6};\n\t"
+        "add.rn.f32x2 cyy, %3, bz;\n\t"
+        "mov.b64 bz, {%7, %7};\n\t"
+        "add.rn.f32x2 czz, %4, bz;\n\t"
+        "mov.b64 {z0, z1}, czz;\n\t"
+        "rcp.approx.ftz.f32 r0, z0;\n\t"
+        "rcp.approx.ftz.f32 r1, z1;\n\t"
+        "mov.b64 rr, {r0, r1};\n\t"
+        "mov.b64 bk, {%8, %8};\n\t"
+        "mul.rn.f32x2 kk, rr, bk;\n\t"
+        "mov.b64 bk, {%10, %10};\n\t"
+        "fma.rn.f32x2 ua, cxx, kk, bk;\n\t"
+        "mov.b64 bk, {%9, %9};\n\t"
+        "mul.rn.f32x2 kk, rr, bk;\n\t"
+        "mov.b64 bk, {%11, %11};\n\t"
+        "fma.rn.f32x2 va, cyy, kk, bk;\n\t"
+        "mov.f32 mg, 0f4B400000;\n\t"
+        "mov.b64 bm, {mg, mg};\n\t"
+        "add.rn.f32x2 tu, ua, bm;\n\t"
+        "add.rn.f32x2 tv, va, bm;\n\t"
+        "sub.rn.f32x2 ru, tu, bm;\n\t"
+        "sub.rn.f32x2 rv, tv, bm;\n\t"
+        "sub.rn.f32x2 du, ua, ru;\n\t"
+        "sub.rn.f32x2 dv, va, rv;\n\t"
+        "mov.b64 bk, {%14, %14};\n\t"
+        "fma.rn.f32x2 fi, rv, bk, tu;\n\t"
+        "mov.b64 bk, {%21, %21};\n\t"
+        "sub.rn.f32x2 qu, ru, bk;\n\t"
+        "mov.b64 bk, {%22, %22};\n\t"
+        "sub.rn.f32x2 qv, rv, bk;\n\t"
+        "mov.b64 {a0, a1}, du;\n\t"
+        "mov.b64 {b0, b1}, dv;\n\t"
+        "mov.b64 {g0, g1}, qu;\n\t"
+        "mov.b64 {h0, h1}, qv;\n\t"
+        "abs.f32 a0, a0;\n\t"
+        "abs.f32 a1, a1;\n\t"
+        "abs.f32 b0, b0;\n\t"
+        "abs.f32 b1, b1;\n\t"
+        "abs.f32 g0, g0;\n\t"
+        "abs.f32 g1, g1;\n\t"
+        "abs.f32 h0, h0;\n\t"
+        "abs.f32 h1, h1;\n\t"
+        "setp.lt.f32 pc0, a0, %12;\n\t"
+        "setp.lt.f32 pc1, a1, %12;\n\t"
+        "setp.lt.and.f32 pc0, b0, %13, pc0;\n\t"
+        "setp.lt.and.f32 pc1, b1, %13, pc1;\n\t"
+        "setp.gt.f32 pp0, z0, 0f00000000;\n\t"
+        "setp.gt.f32 pp1, z1, 0f00000000;\n\t"
+        "setp.le.and.f32 pg0, g0, %21, pc0;\n\t"
+        "setp.le.and.f32 pg1, g1, %21, pc1;\n\t"
+        "setp.le.and.f32 pg0, h0, %22, pg0;\n\t"
+        "setp.le.and.f32 pg1, h1, %22, pg1;\n\t"
+        "and.pred pg0, pg0, pp0;\n\t"
+        "and.pred pg1, pg1, pp1;\n\t"
+        "mov.b64 {i0, i1}, fi;\n\t"
+        "mov.b32 n0, i0;\n\t"
+        "mov.b32 n1, i1;\n\t"
+        "mad.wide.u32 ad0, n0, 4, %15;\n\t"
+        "mad.wide.u32 ad1, n1, 4, %15;\n\t"
+        "mov.f32 d0, 0fFF800000;\n\t"
+        "mov.f32 d1, 0fFF800000;\n\t"
+        "@pg0 ld.global.nc.L2::cache_hint.f32 d0, [ad0], %23;\n\t"
+        "@pg1 ld.global.nc.L2::cache_hint.f32 d1, [ad1], %23;\n\t"
+        "mov.b64 dd, {d0, d1};\n\t"
+        "sub.rn.f32x2 ee, dd, czz;\n\t"
+        "mov.b64 {e0, e1}, ee;\n\t"
+        "setp.ge.f32 pf0, e0, %16;\n\t"
+        "setp.ge.f32 pf1, e1, %16;\n\t"
+        "@pf0 add.u32 %0, %0, %17;\n\t"
+        "@pf1 add.u32 %0, %0, %18;\n\t"
+        "abs.f32 e0, e0;\n\t"
+        "abs.f32 e1, e1;\n\t"
+        "setp.lt.f32 pb0, e0, %16;\n\t"
+        "setp.lt.f32 pb1, e1, %16;\n\t"
+        "not.pred pc0, pc0;\n\t"
+        "not.pred pc1, pc1;\n\t"
+        "or.pred pb0, pb0, pc0;\n\t"
+        "or.pred pb1, pb1, pc1;\n\t"
+        "and.pred pb0, pb0, pp0;\n\t"
+        "and.pred pb1, pb1, pp1;\n\t"
+        "@pb0 or.b32 %1, %1, %19;\n\t"
+        "@pb1 or.b32 %1, %1, %20;\n\t"
+        "}"
+        : "+r"(pend), "+r"(exact)
+        : "l"(sx2), "l"(sy2), "l"(sz2), "f"(zx), "f"(zy), "f"(zz), "f"(K.fx), "f"(K.fy), "f"(K.cx), "f"(K.cy),
+          "f"(K.lim_x), "f"(K.lim_y), "f"(im_w_f), "l"(depth_biased), "f"(trunc_margin), "r"(pend_inc0),
+          "r"(pend_inc1), "r"(exact_bit0), "r"(exact_bit1), "f"(half_w), "f"(half_h), "l"(policy));
+  }
+}
+
+#endif  // TSDF_VALIDATION
+
 // demo.cu:63-66.  (t*w + 1)/(w + 1) with t == 1 is exactly 1 (numerator and denominator are
 // the same rounded sum), so the division is skipped for untouched free-space voxels.
 __device__ __forceinline__ void voxel_update(float& t, float& w, float dist) {

@@ -389,6 +389,25 @@ int stream_launch(tsdf_volume* leader, StreamSlot& S, tsdf::StreamLaunch* L, cud
   L->ticket = S.counters + 2 * tsdf::kStreamMaxSegments + 4;
   L->rec_scratch = leader->rec_scratch;
   CK(tsdf::launch_stream_masks(*L, st));
+  static const bool l2_window = getenv("TSDF_L2_WINDOW") && atoi(getenv("TSDF_L2_WINDOW")) == 1;
+  if (l2_window && L->n_jobs == 1) {
+    // A/B switch for profiles/: an L2-persisting access-policy window over the group's depth frames (BASELINE
+    // north_star (2)).  The window cannot follow the chunk the kernel is working on, so with more frames than fit the
+    // persisting carve-out only a hitRatio fraction of the lines is pinned.
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, leader->d.device));
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
+    size_t bytes = (size_t)L->n_frames * L->frame_stride * sizeof(float);
+    if (bytes > (size_t)prop.accessPolicyMaxWindowSize) bytes = (size_t)prop.accessPolicyMaxWindowSize;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.base_ptr = (void*)S.depth;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = bytes > 0 ? fminf(1.0f, (float)prop.persistingL2CacheMaxSize / (float)bytes) : 0.f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+  }
   CK(tsdf::launch_stream_integrate(*L, leader->resident_blocks, st));
   leader->stats.kernel_launches += 3;
   return TSDF_OK;

@@ -191,7 +191,9 @@ __global__ void __launch_bounds__(kStreamMaxSegments) stream_segment_kernel(cons
 // ------------------------------------------------------------------------------------------------
 // The persistent fusion kernel.
 // ------------------------------------------------------------------------------------------------
-template <int MINB>
+// DIAG (validation library only, results are NOT valid): 1 = no TSDF / weight traffic at all, so that every L2 read of
+// the launch is a depth gather (cache evidence in profiles/); 2 = depth gathers with an L2 evict_last cache hint (A/B).
+template <int MINB, int DIAG = 0>
 __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(const __grid_constant__ StreamLaunch L) {
   __shared__ float4 s_ztab[kChunkMax * ZT];        // plane products M8*t2 of every (frame, plane) of the item
   __shared__ float4 s_pose[kChunkMax * 3];         // (m0 m1 m2 tx) (m4 m5 m6 ty) (m8 m9 m10 tz) per frame
@@ -209,6 +211,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
   K.fx = L.fx; K.fy = L.fy; K.cx = L.cx; K.cy = L.cy; K.lim_x = L.lim_x; K.lim_y = L.lim_y;
   const float im_w_f = (float)L.im_w, half_w = 0.5f * (float)(L.im_w - 1), half_h = 0.5f * (float)(L.im_h - 1);
   const int64_t plane = (int64_t)L.dim_y * L.dim_x;
+  [[maybe_unused]] unsigned long long l2_policy = 0ull;
+#ifdef TSDF_VALIDATION
+  if constexpr (DIAG == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_policy));
+#endif
   const unsigned n_seg = (unsigned)(L.n_jobs * L.n_chunks);
 
   // thread 0: ticket of the next item (fetched one item ahead, so the atomic's latency is off the critical path)
@@ -332,10 +338,19 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
             const float4 zt = s_ztab[f * ZT + k];
             unsigned ex = 0u;
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < 2; ++h) {
+#ifdef TSDF_VALIDATION
+              if constexpr (DIAG == 2) {
+                voxel_classify_pair_hint<kInterior>(sx2[h], sy2[h], sz2[h], zt.x, zt.y, zt.z, K, im_w_f, half_w, half_h,
+                                                    depth_biased, L.trunc_margin, 1u << (16 * h), 1u << (16 * h + 8),
+                                                    1u << (2 * h), 1u << (2 * h + 1), pk, ex, l2_policy);
+                continue;
+              }
+#endif
               voxel_classify_pair<kInterior>(sx2[h], sy2[h], sz2[h], zt.x, zt.y, zt.z, K, im_w_f, half_w, half_h,
                                              depth_biased, L.trunc_margin, 1u << (16 * h), 1u << (16 * h + 8),
                                              1u << (2 * h), 1u << (2 * h + 1), pk, ex);
+            }
             exact |= ex << (k * VEC);
           };
           if ((interior_mask >> f) & 1u) {  // warp-uniform
@@ -410,8 +425,13 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
           q1 = __fadd_rn(L.oy, __fmul_rn((float)o_y, L.voxel_size));
           q2 = __fadd_rn(L.oz, __fmul_rn((float)(J.z_begin + zl0 + k), L.voxel_size));
           idx = ((int64_t)(zl0 + k) * L.dim_y + o_y) * (int64_t)L.dim_x + (int64_t)o_xu * VEC + j;
-          t = __ldcg(tsdf + idx);
-          w = __ldcg(weight + idx);
+          if constexpr (DIAG == 1) {
+            t = 1.0f;
+            w = (float)(item >> 26);   // (opaque to the compiler; always 0)
+          } else {
+            t = __ldcg(tsdf + idx);
+            w = __ldcg(weight + idx);
+          }
           apply_pending(t, w, c);
         }
         bool changed = c != 0u;
@@ -433,7 +453,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
             }
           }
         }
-        if (valid && changed) {
+        if (valid && changed && (DIAG != 1 || t == -7.25f)) {   // (DIAG 1: never true, but keeps the evaluations alive)
           __stcg(tsdf + idx, t);
           __stcg(weight + idx, w);
         }
@@ -443,7 +463,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
 
     // ---------------- write-back of the pending counts (certain free-space observations), coalesced ----------------
     // (after the last phase B: the float4 rows are re-read here, so they carry phase B's stores)
-    if (frame_mask != 0u) {  // warp-uniform
+    if (frame_mask != 0u && DIAG != 1) {  // warp-uniform
 #pragma unroll 1
       for (int k = 0; k < ZT; ++k) {
         const unsigned pk = s_pend[k][threadIdx.x];
@@ -553,6 +573,13 @@ cudaError_t launch_stream_cost(const StreamLaunch& L, cudaStream_t s) {
 
 cudaError_t launch_stream_integrate(const StreamLaunch& L, int n_blocks, cudaStream_t s) {
   if (n_blocks < 1) return cudaErrorInvalidValue;
+#ifdef TSDF_VALIDATION
+  if (const char* e = getenv("TSDF_STREAM_DIAG")) {   // diagnostic variants (see stream_integrate_kernel)
+    const int v = atoi(e);
+    if (v == 1) { stream_integrate_kernel<5, 1><<<n_blocks, kBlockThreads, 0, s>>>(L); return cudaGetLastError(); }
+    if (v == 2) { stream_integrate_kernel<5, 2><<<n_blocks, kBlockThreads, 0, s>>>(L); return cudaGetLastError(); }
+  }
+#endif
   switch (stream_min_blocks()) {
     case 4: stream_integrate_kernel<4><<<n_blocks, kBlockThreads, 0, s>>>(L); break;
     case 5: stream_integrate_kernel<5><<<n_blocks, kBlockThreads, 0, s>>>(L); break;

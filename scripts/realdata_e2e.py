@@ -37,6 +37,18 @@ def run(binary, extra, runs):
     return best, out
 
 
+def timed(cmd, runs):
+    best = None
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+        if r.returncode != 0:
+            return None
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
 def points(ply):
     body = ply.split(b"end_header\n", 1)[1]
     return np.frombuffer(body, dtype=np.float32).reshape(-1, 3)
@@ -50,6 +62,14 @@ def main():
     t_ref, ply_ref = run(REF, [], runs)
     t_ours, ply_ours = run(OURS, [], runs)
     t_ours1, ply_ours1 = run(OURS, ["--threads", "1"], runs)
+    t_ctx = timed([str(ROOT / "3dmatch-toolbox_b200" / "bin" / "cuda_ctx_probe")], runs)
+    phases = None
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([str(OURS)] + ARGS + ["--timing"], cwd=tmp, capture_output=True, text=True, timeout=600)
+        try:
+            phases = json.loads([l for l in r.stderr.splitlines() if l.startswith("{")][-1])
+        except Exception:
+            phases = None
     if t_ref is None or t_ours is None:
         print(json.dumps({"error": {"reference": ply_ref if t_ref is None else "ok", "ours": ply_ours if t_ours is None else "ok"}}))
         return
@@ -64,6 +84,9 @@ def main():
         "bin_demo": {"seconds": round(t_ours, 3), "voxel_updates_per_sec": 500 ** 3 * 50 / t_ours,
                      "seconds_one_decoder_thread": round(t_ours1, 3) if t_ours1 else None},
         "wall_time_ratio": round(t_ref / t_ours, 2),
+        "cuda_context_seconds": round(t_ctx, 3) if t_ctx else None,
+        "wall_time_ratio_without_context": round((t_ref - t_ctx) / max(t_ours - t_ctx, 1e-3), 2) if t_ctx else None,
+        "bin_demo_phases": phases,
         "ply": {"reference_points": int(len(a)), "ours_points": int(len(b)), "byte_identical": ply_ref == ply_ours,
                 "points_only_in_reference": len(sa - sb), "points_only_in_ours": len(sb - sa),
                 "note": "the reference binary is the default --fmad=true build with the device powf: voxels on a rounding / "

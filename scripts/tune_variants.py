@@ -18,9 +18,11 @@ cfg = dict(synth.CONFIGS["1024"], frames=F)
 grid = cfg["grid"]
 depth, poses = bench.build_inputs(pkg, cfg, torch.device("cuda", 0), 0, 1, None)
 ref = None
+import os
+VALIDATION = True if os.environ.get("TSDF_USE_VALIDATION") == "1" else None   # None: validation library only for tuning != 0
 for tuning in tunings:
     with pkg.Volume(grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin, synth.CAM_K, max_batch=K,
-                    tuning=tuning) as vol:
+                    tuning=tuning, validation=VALIDATION) as vol:
         vol.integrate_batch(depth, poses)
         times = []
         for _ in range(3):

@@ -110,6 +110,8 @@ def test_cli_gpus_flag_is_byte_identical(tmp_path):
                 "0.0117", "0.0585", "--dim", "256", "--bin", "--gpus", str(g)]
         run = subprocess.run(argv, cwd=d, capture_output=True, text=True, timeout=600)
         assert run.returncode == 0, run.stderr
-        outs[g] = ((d / "tsdf.ply").read_bytes(), (d / "tsdf.bin").read_bytes(), run.stdout)
+        # (NCCL prints its version banner to stdout when NCCL_DEBUG is set in the environment)
+        stdout = "\n".join(l for l in run.stdout.splitlines() if not l.startswith("NCCL version"))
+        outs[g] = ((d / "tsdf.ply").read_bytes(), (d / "tsdf.bin").read_bytes(), stdout)
     (p1, b1, s1), (pn, bn, sn) = outs.values()
     assert len(p1) > 10000 and p1 == pn and b1 == bn and s1 == sn
