@@ -951,9 +951,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-oracle-planes", action="store_true", help="parity block without the CPU oracle planes")
-    ap.add_argument("--oracle-planes-max", type=int, default=0, help="cap on the number of oracle planes (0 = all cuts +-1)")
+    ap.add_argument("--oracle-planes-max", type=int, default=9, help="cap on the number of oracle planes (0 = all cuts +-1)")
     ap.add_argument("--equal-slabs", action="store_true", help="equal-height z-slabs instead of equal-work ones")
-    ap.add_argument("--rebalance", type=int, default=5, help="feedback-balancing warm-up steps for N > 1")
+    ap.add_argument("--rebalance", type=int, default=6, help="feedback-balancing warm-up steps for N > 1")
     ap.add_argument("--base-cost", type=float, default=0.05, help="cost of a fully culled z group relative to the mean group")
     ap.add_argument("--fragments", type=int, default=0, help="frag300: number of fragments (default 256)")
     ap.add_argument("--frag-batch", type=int, default=8, help="frag300: fragments per launch")
