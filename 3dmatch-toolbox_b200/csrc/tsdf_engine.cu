@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -913,12 +914,30 @@ int tsdf_ComputeTDF(const float* voxel_grid_occ, float* voxel_grid_TDF, int voxe
   const int radius = (int)roundf(trunc_margin / voxel_size);  // core/demo.cu:37
   if (radius < 1 || radius > 100) return set_err(TSDF_ERR_ARG, "search radius %d out of range", radius);
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned short* scratch = nullptr;
-  CK(cudaMallocAsync(&scratch, (size_t)n * 2 * sizeof(unsigned short), s));
-  cudaError_t e = tsdf::launch_compute_tdf(voxel_grid_occ, voxel_grid_TDF, scratch, voxel_grid_dim_x, voxel_grid_dim_y,
+  // scratch (two intermediate grids) from a per-device pool that only grows: no allocation in the steady state.
+  // Calls that share a device are serialised on the pool by stream order: the pool remembers the last stream and
+  // makes the next one wait for it.
+  struct Pool { void* ptr = nullptr; size_t bytes = 0; cudaEvent_t last = nullptr; };
+  static Pool pools[64];
+  static std::mutex pool_lock;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return set_err(TSDF_ERR_ARG, "device ordinal out of range");
+  const size_t need = tsdf::compute_tdf_scratch_bytes(voxel_grid_dim_x, voxel_grid_dim_y, voxel_grid_dim_z, radius);
+  std::lock_guard<std::mutex> lock(pool_lock);
+  Pool& P = pools[dev];
+  if (!P.last) CK(cudaEventCreateWithFlags(&P.last, cudaEventDisableTiming));
+  if (need > P.bytes) {
+    if (P.ptr) { CK(cudaEventSynchronize(P.last)); CK(cudaFree(P.ptr)); P.ptr = nullptr; P.bytes = 0; }
+    CK(cudaMalloc(&P.ptr, need));
+    P.bytes = need;
+  } else {
+    CK(cudaStreamWaitEvent(s, P.last, 0));
+  }
+  cudaError_t e = tsdf::launch_compute_tdf(voxel_grid_occ, voxel_grid_TDF, P.ptr, voxel_grid_dim_x, voxel_grid_dim_y,
                                            voxel_grid_dim_z, radius, s);
-  cudaFreeAsync(scratch, s);
   CK(e);
+  CK(cudaEventRecord(P.last, s));
   return TSDF_OK;
 }
 

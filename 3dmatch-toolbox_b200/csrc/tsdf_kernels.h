@@ -154,8 +154,9 @@ cudaError_t launch_extract_scan(unsigned long long* tile_counts, int64_t n_tiles
 cudaError_t launch_extract_emit(const ExtractParams& p, const unsigned long long* tile_offsets, int64_t n_tiles,
                                 float* xyz, cudaStream_t s);
 cudaError_t launch_selftest_rounding(unsigned long long* mismatches, cudaStream_t s);
-// tdf_kernels.cu: scratch = 2 * dim_x*dim_y*dim_z unsigned shorts
-cudaError_t launch_compute_tdf(const float* occ, float* tdf, unsigned short* scratch, int dim_x, int dim_y, int dim_z,
+// tdf_kernels.cu: scratch = compute_tdf_scratch_bytes() bytes of device memory (two intermediate grids, 8 or 16 bit)
+size_t compute_tdf_scratch_bytes(int dim_x, int dim_y, int dim_z, int radius);
+cudaError_t launch_compute_tdf(const float* occ, float* tdf, void* scratch, int dim_x, int dim_y, int dim_z,
                                int radius, cudaStream_t s);
 cudaError_t launch_tdf_scatter_points(const float* pts, int64_t n_pts, float* occ, int dim_x, int dim_y, int dim_z,
                                       float ox, float oy, float oz, float voxel_size, cudaStream_t s);

@@ -211,3 +211,74 @@ def refine_group_cost(group_cost, ranges, rank_ms, base_cost: float = 0.05, damp
     scale = np.interp(np.arange(len(cost)), centers, ratio)
     # scale the effective cost, then take the base part out again so that split_groups() adds it back unchanged
     return np.maximum(eff * scale - base_cost * cost.mean(), 0.0)
+
+
+# ---- plane-granular variant (bench.py): a group of 8 planes next to the far wall is ~6 % of a rank's work at 8 GPUs,
+#      so the feedback loop needs finer cuts than tsdf_split_slabs' multiples of 8 (slab tiles are laid out relative to
+#      the slab's first plane, so any cut is legal)
+
+def plane_cost_from_groups(group_cost, dim_z: int, base_cost: float = 0.05) -> np.ndarray:
+    """Per-plane cost model from the per-group cull statistics: a group's count spread over its planes, plus the
+    base cost of a culled plane (relative to the mean)."""
+    g = np.maximum(np.asarray(group_cost, dtype=np.float64), 0.0)
+    per_plane = np.repeat(g / 8.0, 8)[:dim_z]
+    return per_plane + base_cost * max(per_plane.mean(), 1e-300)
+
+
+def split_planes(plane_cost, world: int):
+    """Contiguous slabs of (nearly) equal summed cost, cut at single planes; every slab keeps at least one plane."""
+    cost = np.maximum(np.asarray(plane_cost, dtype=np.float64), 0.0) + 1e-12
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    dim_z = len(cost)
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        z = int(np.searchsorted(cum, target))
+        if z > 0 and target - cum[z - 1] < cum[z] - target:
+            z -= 1
+        cuts.append(min(max(z, cuts[-1] + 1), dim_z - (world - r)))
+    cuts.append(dim_z)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def refine_plane_cost_piecewise(plane_cost, ranges, rank_ms, damping: float = 1.0) -> np.ndarray:
+    """Feedback balancing: every slab's planes are scaled by (measured time / modelled cost) of that slab, so the model
+    reproduces the measured rank times of the current partition exactly (damping = 1); what remains is the distribution
+    INSIDE each slab, which the next measurement corrects."""
+    cost = np.asarray(plane_cost, dtype=np.float64).copy()
+    model = np.array([cost[a:b].sum() for a, b in ranges])
+    ratio = np.asarray(rank_ms, dtype=np.float64) / np.maximum(model, 1e-300)
+    ratio = (ratio / ratio.mean()) ** damping
+    for (a, b), r in zip(ranges, ratio):
+        cost[a:b] *= r
+    return cost
+
+
+def fit_plane_cost(prior, history, reg: float = 0.02) -> np.ndarray:
+    """Per-plane cost from ALL partitions measured so far.  `history`: list of (ranges, rank_ms).  The cuts of all
+    partitions split [0, dim_z) into intervals; inside an interval the cost keeps the prior's shape and gets one
+    scale factor, and the factors are the least-squares solution of `sum over the slab's intervals = measured rank
+    time` over every measurement (weakly regularised towards one common scale).  Planes that moved from one slab to
+    its neighbour between two partitions are thereby costed from the DIFFERENCE of the two measurements, which is what
+    locates a thin expensive band (the far wall) inside a slab."""
+    prior = np.maximum(np.asarray(prior, dtype=np.float64), 1e-300)
+    dim_z = len(prior)
+    cuts = sorted({0, dim_z} | {int(a) for ranges, _ in history for a, _ in ranges})
+    iv = list(zip(cuts[:-1], cuts[1:]))
+    P = np.array([prior[a:b].sum() for a, b in iv])
+    rows, rhs = [], []
+    for ranges, t in history:
+        for (a, b), tr in zip(ranges, t):
+            rows.append(np.array([P[j] if (a <= lo and hi <= b) else 0.0 for j, (lo, hi) in enumerate(iv)]))
+            rhs.append(float(tr))
+    A, y = np.array(rows), np.array(rhs)
+    s0 = y.sum() / max(A.sum(), 1e-300)
+    w = reg * np.sqrt(len(rows) / max(len(iv), 1))
+    A2 = np.vstack([A, w * np.diag(P)])
+    y2 = np.concatenate([y, w * P * s0])
+    sol, *_ = np.linalg.lstsq(A2, y2, rcond=None)
+    sol = np.clip(sol, 0.05 * s0, None)
+    out = prior.copy()
+    for (a, b), sj in zip(iv, sol):
+        out[a:b] *= sj
+    return out

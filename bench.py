@@ -280,6 +280,10 @@ def run_volume(args, D):
         cfg["frames"] = args.frames
     grid, F = cfg["grid"], cfg["frames"]
     dim_z = grid.dims[2]
+    # every rank watches its own GPU; started first (nvidia-smi needs seconds to produce its first line on an 8-GPU box,
+    # longer than the timed region of a multi-GPU run)
+    sampler = ClockSampler(D.local_rank)
+    sampler.start()
     depth, poses = build_inputs(pkg, cfg, device, rank, world, D.dist)
 
     def make_volume(z_range, batch=None):
@@ -296,7 +300,8 @@ def run_volume(args, D):
         group_cost = pkg.plan_z_cost(grid.dims, grid.origin, grid.voxel_size, grid.trunc_margin, synth.CAM_K, depth, poses,
                                      device=D.local_rank, frame_step=max(1, F // 128), cull_level=args.cull).astype(np.float64)
         plan_ms = (time.perf_counter() - t0) * 1e3
-        ranges = sharding.split_groups(group_cost, dim_z, world, args.base_cost)
+        plane_cost = sharding.plane_cost_from_groups(group_cost, dim_z, args.base_cost)
+        ranges = sharding.split_planes(plane_cost, world)
 
     def make_warm_volume(z_range):
         """A volume whose lazy allocations (frame store, masks, item lists) have already happened, so that the first
@@ -326,8 +331,10 @@ def run_volume(args, D):
                 best = (max(rank_t), ranges)
             if max(rank_t) / (sum(rank_t) / world) < 1.015:
                 break
-            group_cost = sharding.refine_group_cost(group_cost, ranges, rank_t, args.base_cost, damping=0.8)
-            new_ranges = sharding.split_groups(group_cost, dim_z, world, args.base_cost)
+            # (slightly over-relaxed at first: the plan knows the frusta and the occlusion but not the cost of the
+            #  surface band, which sits in one thin layer of the last slab)
+            plane_cost = sharding.refine_plane_cost_piecewise(plane_cost, ranges, rank_t, damping=1.4 if len(rebalance_log) <= 3 else 1.0)
+            new_ranges = sharding.split_planes(plane_cost, world)
             if new_ranges == ranges:
                 break
             switch_to(new_ranges)
@@ -342,8 +349,6 @@ def run_volume(args, D):
         vol.integrate_batch(depth, poses)
 
     # ---- value: inputs resident in HBM --------------------------------------------------------------
-    sampler = ClockSampler(D.local_rank)   # every rank watches its own GPU
-    sampler.start()
     for _ in range(args.warmup):
         step_device()
     D.barrier()
@@ -953,7 +958,7 @@ def main():
     ap.add_argument("--no-oracle-planes", action="store_true", help="parity block without the CPU oracle planes")
     ap.add_argument("--oracle-planes-max", type=int, default=9, help="cap on the number of oracle planes (0 = all cuts +-1)")
     ap.add_argument("--equal-slabs", action="store_true", help="equal-height z-slabs instead of equal-work ones")
-    ap.add_argument("--rebalance", type=int, default=6, help="feedback-balancing warm-up steps for N > 1")
+    ap.add_argument("--rebalance", type=int, default=10, help="feedback-balancing warm-up steps for N > 1")
     ap.add_argument("--base-cost", type=float, default=0.05, help="cost of a fully culled z group relative to the mean group")
     ap.add_argument("--fragments", type=int, default=0, help="frag300: number of fragments (default 256)")
     ap.add_argument("--frag-batch", type=int, default=8, help="frag300: fragments per launch")
