@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "tsdf_point_cloud_to_tdf", "tsdf_integrate_multi", "tsdf_plan_z_cost", "tsdf_get_z_cost", "tsdf_split_slabs",
     "tsdf_sharded_create", "tsdf_sharded_destroy", "tsdf_sharded_reset", "tsdf_sharded_synchronize",
     "tsdf_sharded_integrate_batch", "tsdf_sharded_extract_surface", "tsdf_sharded_copy_surface", "tsdf_sharded_write_bin",
-    "tsdf_sharded_slab",
+    "tsdf_sharded_slab", "tsdf_copy_surface_normals",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library(validation: bool = False) -> C.CDLL:
         "tsdf_device_ptrs": [vp, C.POINTER(vp), C.POINTER(vp)],
         "tsdf_extract_surface": [vp, C.c_float, C.c_float, i64p],
         "tsdf_copy_surface": [vp, vp, C.c_int64],
+        "tsdf_copy_surface_normals": [vp, vp, C.c_int64],
         "tsdf_surface_device_ptr": [vp, C.POINTER(vp), i64p],
         "tsdf_write_ply": [C.c_char_p, vp, C.c_int64],
         "tsdf_write_bin": [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,
@@ -458,6 +459,13 @@ class Volume:
             out = np.empty((n, 3), np.float32)
         _check(self._lib.tsdf_copy_surface(self._h, _ptr(out), n), "tsdf_copy_surface")
         return out[:n] if isinstance(out, np.ndarray) else out
+
+    def surface_normals(self) -> np.ndarray:
+        """Unit normals of the points of the last extract_surface(), same order (N, 3)."""
+        _, n = self.surface_device_ptr()
+        out = np.zeros((n, 3), np.float32)
+        _check(self._lib.tsdf_copy_surface_normals(self._h, out.ctypes.data, n), "tsdf_copy_surface_normals")
+        return out
 
     def surface_device_ptr(self):
         p, n = C.c_void_p(), C.c_int64(0)

@@ -659,6 +659,8 @@ void tsdf_destroy(tsdf_volume* v) {
   if (v->owns_volume) { cudaFree(v->tsdf); cudaFree(v->weight); }
   cudaFree(v->tile_offsets);
   cudaFree(v->xyz);
+  cudaFree(v->vidx);
+  cudaFree(v->normals);
   if (v->t0) cudaEventDestroy(v->t0);
   if (v->t1) cudaEventDestroy(v->t1);
   if (v->owns_stream && v->stream) cudaStreamDestroy(v->stream);
@@ -811,13 +813,16 @@ int tsdf_extract_surface(tsdf_volume* v, float tsdf_thresh, float weight_thresh,
   v->stats.d2h_bytes += sizeof total;
   if ((int64_t)total > v->xyz_cap) {
     cudaFree(v->xyz);
+    cudaFree(v->vidx);
     v->xyz = nullptr;
+    v->vidx = nullptr;
     v->xyz_cap = 0;
     CK(cudaMalloc(&v->xyz, (size_t)total * 3 * sizeof(float)));
+    CK(cudaMalloc(&v->vidx, (size_t)total * sizeof(long long)));
     v->xyz_cap = (int64_t)total;
   }
   if (total > 0) {
-    CK(tsdf::launch_extract_emit(p, v->tile_offsets, n_tiles, v->xyz, v->stream));
+    CK(tsdf::launch_extract_emit(p, v->tile_offsets, n_tiles, v->xyz, v->vidx, v->stream));
     v->stats.kernel_launches += 1;
   }
   v->n_points = (int64_t)total;
@@ -834,6 +839,33 @@ int tsdf_copy_surface(tsdf_volume* v, float* xyz_host, int64_t capacity_points) 
   if (int rc = use_device(v)) return rc;
   const size_t bytes = (size_t)v->n_points * 3 * sizeof(float);
   CK(cudaMemcpyAsync(xyz_host, v->xyz, bytes, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaStreamSynchronize(v->stream));
+  v->stats.d2h_bytes += bytes;
+  return TSDF_OK;
+}
+
+int tsdf_copy_surface_normals(tsdf_volume* v, float* normals_host, int64_t capacity_points) {
+  if (!v) return set_err(TSDF_ERR_ARG, "handle is NULL");
+  if (v->n_points < 0) return set_err(TSDF_ERR_STATE, "tsdf_extract_surface has not been called since the last update");
+  if (capacity_points < v->n_points) return set_err(TSDF_ERR_ARG, "capacity %lld < %lld points", (long long)capacity_points, (long long)v->n_points);
+  if (v->n_points == 0) return TSDF_OK;
+  if (!normals_host) return set_err(TSDF_ERR_ARG, "normals_host is NULL");
+  if (int rc = use_device(v)) return rc;
+  if (v->normals_cap < v->n_points) {
+    cudaFree(v->normals);
+    v->normals = nullptr;
+    v->normals_cap = 0;
+    CK(cudaMalloc(&v->normals, (size_t)v->n_points * 3 * sizeof(float)));
+    v->normals_cap = v->n_points;
+  }
+  tsdf::ExtractParams p;
+  memset(&p, 0, sizeof p);
+  p.tsdf = v->tsdf; p.weight = v->weight; p.n = v->n_vox;
+  p.dim_x = (int)v->d.dim_x; p.dim_y = (int)v->d.dim_y; p.z_begin = (int)v->d.z_begin;
+  CK(tsdf::launch_surface_normals(p, v->nz, v->vidx, v->n_points, v->normals, v->stream));
+  v->stats.kernel_launches += 1;
+  const size_t bytes = (size_t)v->n_points * 3 * sizeof(float);
+  CK(cudaMemcpyAsync(normals_host, v->normals, bytes, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaStreamSynchronize(v->stream));
   v->stats.d2h_bytes += bytes;
   return TSDF_OK;

@@ -94,7 +94,10 @@ struct tsdf_volume {
   unsigned long long* tile_offsets = nullptr;
   int64_t tile_cap = 0;
   float* xyz = nullptr;
-  int64_t xyz_cap = 0, n_points = -1;
+  long long* vidx = nullptr;     // slab-local linear voxel index of every extracted point
+  float* normals = nullptr;
+  int64_t xyz_cap = 0, normals_cap = 0, n_points = -1;
+  float last_tsdf_thresh = 0.f, last_weight_thresh = 0.f;
   // timing / stats
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   tsdf_stats stats = {};

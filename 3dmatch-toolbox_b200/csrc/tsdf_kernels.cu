@@ -932,7 +932,7 @@ extract_scan_kernel(unsigned long long* __restrict__ tile_counts, int64_t n_tile
 
 __global__ void __launch_bounds__(kBlockThreads)
 extract_emit_kernel(const __grid_constant__ ExtractParams P, const unsigned long long* __restrict__ tile_offsets,
-                    int64_t n_tiles, float* __restrict__ xyz) {
+                    int64_t n_tiles, float* __restrict__ xyz, long long* __restrict__ voxel_index) {
   __shared__ unsigned s_cnt[kExtractRounds][kBlockThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t plane = (int64_t)P.dim_x * P.dim_y;
@@ -972,7 +972,9 @@ extract_emit_kernel(const __grid_constant__ ExtractParams P, const unsigned long
           const int64_t rem = i - z * plane;
           const int yy = (int)(rem / P.dim_x);
           const int xx = (int)(rem - (int64_t)yy * P.dim_x);
-          float* out = xyz + 3ull * (tile_base + run + before + my_rank[r]);
+          const unsigned long long rank = tile_base + run + before + my_rank[r];
+          if (voxel_index != nullptr) voxel_index[rank] = (long long)i;
+          float* out = xyz + 3ull * rank;
           out[0] = __fadd_rn(P.ox, __fmul_rn((float)xx, P.voxel_size));
           out[1] = __fadd_rn(P.oy, __fmul_rn((float)yy, P.voxel_size));
           out[2] = __fadd_rn(P.oz, __fmul_rn((float)(z + P.z_begin), P.voxel_size));
@@ -982,6 +984,35 @@ extract_emit_kernel(const __grid_constant__ ExtractParams P, const unsigned long
     }
     __syncthreads();
   }
+}
+
+// Surface normals: the normalised central difference of the TSDF at a surface voxel, as
+// PCL-benchmark/pclWrapperFPFH.h:308-330 (computeSurfaceNormal) computes it; mLib's getNormalized() is
+// val = 1 / sqrt(x*x + y*y + z*z), (x*val, y*val, z*val).  (0, 0, 0) where a neighbour lies outside the slab or the
+// gradient vanishes.
+__global__ void __launch_bounds__(256) surface_normals_kernel(const __grid_constant__ ExtractParams P, int64_t nz,
+                                                              const long long* __restrict__ voxel_index, int64_t n,
+                                                              float* __restrict__ normals) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int64_t i = voxel_index[p];
+  const int64_t plane = (int64_t)P.dim_x * P.dim_y;
+  const int64_t z = i / plane, rem = i - z * plane;
+  const int y = (int)(rem / P.dim_x), x = (int)(rem - (int64_t)y * P.dim_x);
+  float nx = 0.0f, ny = 0.0f, nzv = 0.0f;
+  if (x > 0 && x < P.dim_x - 1 && y > 0 && y < P.dim_y - 1 && z > 0 && z < nz - 1) {
+    const float gx = __fsub_rn(__ldg(P.tsdf + i + 1), __ldg(P.tsdf + i - 1));
+    const float gy = __fsub_rn(__ldg(P.tsdf + i + P.dim_x), __ldg(P.tsdf + i - P.dim_x));
+    const float gz = __fsub_rn(__ldg(P.tsdf + i + plane), __ldg(P.tsdf + i - plane));
+    if (!(gx == 0.0f && gy == 0.0f && gz == 0.0f)) {
+      const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+      const float val = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+      nx = __fmul_rn(gx, val); ny = __fmul_rn(gy, val); nzv = __fmul_rn(gz, val);
+    }
+  }
+  normals[3 * p + 0] = nx;
+  normals[3 * p + 1] = ny;
+  normals[3 * p + 2] = nzv;
 }
 
 // All 2^32 float bit patterns: round_pixel() vs roundf() + the reference's bounds test.
@@ -1236,9 +1267,16 @@ cudaError_t launch_extract_scan(unsigned long long* tile_counts, int64_t n_tiles
 }
 
 cudaError_t launch_extract_emit(const ExtractParams& p, const unsigned long long* tile_offsets, int64_t n_tiles,
-                                float* xyz, cudaStream_t s) {
+                                float* xyz, long long* voxel_index, cudaStream_t s) {
   const int blocks = (int)(n_tiles < 148 * 16 ? n_tiles : 148 * 16);
-  extract_emit_kernel<<<blocks > 0 ? blocks : 1, kBlockThreads, 0, s>>>(p, tile_offsets, n_tiles, xyz);
+  extract_emit_kernel<<<blocks > 0 ? blocks : 1, kBlockThreads, 0, s>>>(p, tile_offsets, n_tiles, xyz, voxel_index);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_surface_normals(const ExtractParams& p, int64_t nz, const long long* voxel_index, int64_t n,
+                                   float* normals, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  surface_normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, nz, voxel_index, n, normals);
   return cudaGetLastError();
 }
 

@@ -152,7 +152,10 @@ cudaError_t launch_extract_count(const ExtractParams& p, unsigned long long* til
 cudaError_t launch_extract_scan(unsigned long long* tile_counts, int64_t n_tiles, unsigned long long* total,
                                 cudaStream_t s);
 cudaError_t launch_extract_emit(const ExtractParams& p, const unsigned long long* tile_offsets, int64_t n_tiles,
-                                float* xyz, cudaStream_t s);
+                                float* xyz, long long* voxel_index, cudaStream_t s);
+// Unit normals (normalised central TSDF differences) of n surface voxels given by their slab-local linear indices.
+cudaError_t launch_surface_normals(const ExtractParams& p, int64_t nz, const long long* voxel_index, int64_t n,
+                                   float* normals, cudaStream_t s);
 cudaError_t launch_selftest_rounding(unsigned long long* mismatches, cudaStream_t s);
 // tdf_kernels.cu: scratch = compute_tdf_scratch_bytes() bytes of device memory (two intermediate grids, 8 or 16 bit)
 size_t compute_tdf_scratch_bytes(int dim_x, int dim_y, int dim_z, int radius);

@@ -163,6 +163,10 @@ int tsdf_device_ptrs(tsdf_volume *v, float **tsdf_dev, float **weight_dev);
  * on the device until tsdf_copy_surface. */
 int tsdf_extract_surface(tsdf_volume *v, float tsdf_thresh, float weight_thresh, int64_t *n_points);
 int tsdf_copy_surface(tsdf_volume *v, float *xyz_host, int64_t capacity_points);
+/* Unit surface normals of the points of the last tsdf_extract_surface, in the same order: the
+ * normalised central difference of the TSDF at the voxel, as PCL-benchmark/pclWrapperFPFH.h:308-330
+ * (computeSurfaceNormal) computes it; (0, 0, 0) where a neighbour lies outside the slab or the gradient vanishes. */
+int tsdf_copy_surface_normals(tsdf_volume *v, float *normals_host, int64_t capacity_points);
 /* Device buffer of the extracted points.  The call waits for the extraction kernels (they run on the engine's own
  * stream), so the buffer may be read from any stream afterwards; it stays valid until the next tsdf_extract_surface,
  * integrate, reset or destroy on this handle. */

@@ -53,6 +53,7 @@ def _p(a):
 def lib():
     L = _load(ORACLE_LIB)
     L.oracle_extract_surface.restype = C.c_int64
+    L.oracle_surface_normals.restype = C.c_int64
     return L
 
 
@@ -124,6 +125,18 @@ def extract_surface(tsdf, weight, dims, origin, voxel_size, tsdf_thresh=0.2, wei
     if n:
         lib().oracle_extract_surface(*args, _p(xyz))
     return xyz
+
+
+def surface_normals(tsdf, weight, tsdf_thresh=0.2, weight_thresh=1.0):
+    """One unit normal per surface voxel of the [nz, dy, dx] slab, in extract_surface order (parity unpinned)."""
+    t, w = _f32(tsdf), _f32(weight)
+    nz, dy, dx = t.shape
+    n = int(((np.abs(t) < np.float32(tsdf_thresh)) & (w > np.float32(weight_thresh))).sum())
+    out = np.zeros((n, 3), np.float32)
+    got = lib().oracle_surface_normals(_p(t), _p(w), C.c_int64(dx), C.c_int64(dy), C.c_int64(nz), C.c_float(tsdf_thresh),
+                                       C.c_float(weight_thresh), _p(out))
+    assert got == n
+    return out
 
 
 def write_ply(path, xyz):

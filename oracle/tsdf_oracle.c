@@ -241,6 +241,40 @@ int64_t oracle_extract_surface(const float *tsdf, const float *weight,
     return count;
 }
 
+/* Surface normals, parity UNPINNED: the only reference code is
+ * PCL-benchmark/pclWrapperFPFH.h:308-330 (computeSurfaceNormal): central differences of the TSDF at the voxel,
+ * normalised with mLib's vec3f::getNormalized() -- mLib (niessner/mLib, not vendored in the reference tree) computes
+ * `val = 1.0f / sqrtf(x*x + y*y + z*z); (x*val, y*val, z*val)`; restated here with one rounding per operation.
+ * One normal per surface voxel of the slab, in the order of oracle_extract_surface; (0, 0, 0) where a neighbour lies
+ * outside the slab (isValidCoordinate fails, :309-315) or the gradient is zero (:320). */
+int64_t oracle_surface_normals(const float *tsdf, const float *weight, int64_t dim_x, int64_t dim_y, int64_t nz,
+                               float tsdf_thresh, float weight_thresh, float *normals)
+{
+    int64_t n = nz * dim_y * dim_x, plane = dim_x * dim_y;
+    int64_t count = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (fabsf(tsdf[i]) < tsdf_thresh && weight[i] > weight_thresh) {
+            int64_t z = i / plane, rem = i - z * plane, y = rem / dim_x, x = rem - y * dim_x;
+            float nx = 0.0f, ny = 0.0f, nzv = 0.0f;
+            if (x > 0 && x < dim_x - 1 && y > 0 && y < dim_y - 1 && z > 0 && z < nz - 1) {
+                float gx = tsdf[i + 1] - tsdf[i - 1];
+                float gy = tsdf[i + dim_x] - tsdf[i - dim_x];
+                float gz = tsdf[i + plane] - tsdf[i - plane];
+                if (!(gx == 0.0f && gy == 0.0f && gz == 0.0f)) {
+                    float len2 = (gx * gx + gy * gy) + gz * gz;
+                    float val = 1.0f / sqrtf(len2);
+                    nx = gx * val; ny = gy * val; nzv = gz * val;
+                }
+            }
+            normals[3 * count + 0] = nx;
+            normals[3 * count + 1] = ny;
+            normals[3 * count + 2] = nzv;
+            ++count;
+        }
+    }
+    return count;
+}
+
 /* utils.hpp:26-33 header, :50-52 payload */
 int oracle_write_ply(const char *path, const float *xyz, int64_t n_points)
 {

@@ -56,6 +56,8 @@ void oracle_depth_from_u16(const uint16_t *mm, int64_t n, float *depth);
 
 /* utils.hpp:20-23 / :36-53 on the slab [z_begin, z_end): count, then emit xyz triples in
  * ascending linear index.  xyz may be NULL (count only).  Returns the number of points. */
+int64_t oracle_surface_normals(const float *tsdf, const float *weight, int64_t dim_x, int64_t dim_y, int64_t nz,
+                               float tsdf_thresh, float weight_thresh, float *normals);
 int64_t oracle_extract_surface(const float *tsdf, const float *weight,
                                int64_t dim_x, int64_t dim_y, int64_t dim_z,
                                int64_t z_begin, int64_t z_end,

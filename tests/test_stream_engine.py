@@ -215,3 +215,20 @@ def test_plan_z_cost_matches_engine_statistics_and_balances(pkg, sequence):
     assert max(part) / (sum(part) / 4) < max(eq) / (sum(eq) / 4)
     sub = pkg.plan_z_cost(dims, ORIGIN, voxel, trunc, K, depth, poses, frame_step=4)
     assert 0.15 * cost.sum() < sub.sum() < 0.4 * cost.sum()
+
+
+def test_surface_normals_vs_oracle(pkg, oracle, sequence):
+    """SURVEY 8f row 4 (parity unpinned: no reference fixture; the algorithm is PCL-benchmark/pclWrapperFPFH.h:308-330
+    + mLib's getNormalized): normals of the extracted surface voxels against the oracle restatement, bit for bit."""
+    depth, _, poses, K = sequence(list(range(0, 60, 4)))
+    dims, voxel, trunc = (128, 120, 96), 0.0234, 0.117
+    with pkg.Volume(dims, ORIGIN, voxel, trunc, K) as vol:
+        vol.integrate_batch(depth, poses)
+        t, w = vol.download()
+        pts = vol.extract_surface()
+        nrm = vol.surface_normals()
+    ref = oracle.surface_normals(t, w)
+    assert nrm.shape == ref.shape == pts.shape and len(pts) > 5000
+    assert_bit_equal(nrm, ref, "surface normals")
+    length = np.linalg.norm(nrm.astype(np.float64), axis=1)
+    assert ((np.abs(length - 1) < 1e-6) | (length == 0)).all() and (length > 0).mean() > 0.9
