@@ -193,13 +193,16 @@ __global__ void __launch_bounds__(kStreamMaxSegments) stream_segment_kernel(cons
 // ------------------------------------------------------------------------------------------------
 // DIAG (validation library only, results are NOT valid): 1 = no TSDF / weight traffic at all, so that every L2 read of
 // the launch is a depth gather (cache evidence in profiles/); 2 = depth gathers with an L2 evict_last cache hint (A/B).
-template <int MINB, int DIAG = 0>
+// WARPB: phase B per WARP (each warp evaluates the sticky voxels of its own tile right after its own phase A; no block
+// barrier inside an item) instead of pooled over the block (full lanes, one barrier per epoch).
+template <int MINB, int DIAG = 0, bool WARPB = false>
 __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(const __grid_constant__ StreamLaunch L) {
   __shared__ float4 s_ztab[kChunkMax * ZT];        // plane products M8*t2 of every (frame, plane) of the item
   __shared__ float4 s_pose[kChunkMax * 3];         // (m0 m1 m2 tx) (m4 m5 m6 ty) (m8 m9 m10 tz) per frame
   __shared__ unsigned s_pend[ZT][kBlockThreads];   // byte j of [k][t]: pending free-space updates of voxel (j, k) of thread t
   __shared__ unsigned s_wmask[kWarps];
   __shared__ unsigned s_rec_count[3];              // record counters, rotating over the epochs
+  __shared__ unsigned s_wcount[kWarps];            // WARPB: record counter of every warp
   __shared__ unsigned s_hdr[4];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
     const unsigned frame_mask = wm2.x, interior_mask = wm2.y;
     if (lane == 0) s_wmask[warp] = frame_mask;
     if (threadIdx.x == 0) s_rec_count[0] = s_rec_count[1] = s_rec_count[2] = 0u;
+    if (lane == 0) s_wcount[warp] = 0u;
     for (int e = threadIdx.x; e < nf * ZT; e += kBlockThreads) {
       const int f = e / ZT, k = e - f * ZT;
       const FramePose ps = poses[f];
@@ -306,9 +310,11 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
     unsigned n_epoch = 0u;
     for (int e0 = 0; e0 < nf; e0 += L.epoch) {
       const unsigned epoch_bits = ((L.epoch >= 32) ? 0xffffffffu : ((1u << L.epoch) - 1u)) << e0;
-      if ((block_mask & epoch_bits) == 0u) continue;  // block-uniform
+      if (((WARPB ? frame_mask : block_mask) & epoch_bits) == 0u) continue;  // block-uniform (WARPB: warp-uniform)
       const unsigned slot = n_epoch % 3u;
-      unsigned* const rec = rec_base + (n_epoch & 1u) * kRecCap;
+      // block mode: two lists alternating over the epochs; WARPB: one list of 1024 records (= voxels of a warp tile) per warp
+      unsigned* const rec = WARPB ? rec_base + warp * (kRecCap / kWarps) : rec_base + (n_epoch & 1u) * kRecCap;
+      unsigned* const counter = WARPB ? &s_wcount[warp] : &s_rec_count[slot];
       ++n_epoch;
 
       // ---------------- phase A: classification, per warp ----------------
@@ -371,7 +377,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
         }
         unsigned fresh = exact & ~sticky;
         if (fresh != 0u) {
-          unsigned pos = atomicAdd(&s_rec_count[slot], (unsigned)__popc(fresh));
+          unsigned pos = atomicAdd(counter, (unsigned)__popc(fresh));
           while (fresh != 0u) {
             const unsigned s = (unsigned)(__ffs(fresh) - 1);
             fresh &= fresh - 1u;
@@ -398,14 +404,14 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
           }
         }
       }
-      __syncthreads();  // the epoch's records are complete
+      if constexpr (WARPB) __syncwarp(); else __syncthreads();  // the epoch's records are complete
 
       // ---------------- phase B: sticky voxels, one record per thread, frames in ascending order ----------------
-      const unsigned n_rec = s_rec_count[slot];
-      // the counter of the epoch after the next one: last read in the previous epoch's phase B, i.e. before this barrier;
-      // first written after the next epoch's barrier
-      if (threadIdx.x == 0) s_rec_count[(slot + 2u) % 3u] = 0u;
-      for (unsigned base = (unsigned)warp * 32u; base < n_rec; base += kBlockThreads) {  // warp-uniform trip count
+      const unsigned n_rec = *counter;
+      // block mode: the counter of the epoch after the next one was last read in the previous epoch's phase B, i.e.
+      // before this barrier, and is first written after the next epoch's barrier
+      if (!WARPB && threadIdx.x == 0) s_rec_count[(slot + 2u) % 3u] = 0u;
+      for (unsigned base = WARPB ? 0u : (unsigned)warp * 32u; base < n_rec; base += (WARPB ? 32u : (unsigned)kBlockThreads)) {  // warp-uniform trip count
         const unsigned i = base + (unsigned)lane;
         const bool valid = i < n_rec;
         unsigned wm = 0u, c = 0u;
@@ -458,8 +464,14 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
           __stcg(weight + idx, w);
         }
       }
+      if constexpr (WARPB) {   // the warp's list is free again
+        __syncwarp();
+        if (lane == 0) *counter = 0u;
+        __syncwarp();
+      }
     }
-    __syncthreads();  // every phase B store of the block precedes the write-back's loads
+    // every phase B store precedes the write-back's loads (WARPB: both touch only this warp's own voxels)
+    if constexpr (WARPB) __syncwarp(); else __syncthreads();
 
     // ---------------- write-back of the pending counts (certain free-space observations), coalesced ----------------
     // (after the last phase B: the float4 rows are re-read here, so they carry phase B's stores)
@@ -580,6 +592,11 @@ cudaError_t launch_stream_integrate(const StreamLaunch& L, int n_blocks, cudaStr
     if (v == 2) { stream_integrate_kernel<5, 2><<<n_blocks, kBlockThreads, 0, s>>>(L); return cudaGetLastError(); }
   }
 #endif
+  static const bool warpb = getenv("TSDF_STREAM_WARPB") && atoi(getenv("TSDF_STREAM_WARPB")) == 1;
+  if (warpb) {   // A/B switch: phase B per warp instead of pooled over the block
+    stream_integrate_kernel<5, 0, true><<<n_blocks, kBlockThreads, 0, s>>>(L);
+    return cudaGetLastError();
+  }
   switch (stream_min_blocks()) {
     case 4: stream_integrate_kernel<4><<<n_blocks, kBlockThreads, 0, s>>>(L); break;
     case 5: stream_integrate_kernel<5><<<n_blocks, kBlockThreads, 0, s>>>(L); break;
