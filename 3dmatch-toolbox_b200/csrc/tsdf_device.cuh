@@ -643,14 +643,16 @@ struct Row<1> {
 // covers every voxel inside it.
 struct CullAccum {
   bool behind, left, right, top, bottom;
-  float cz_min, u_min, u_max, v_min, v_max;  // for the occlusion test (valid when cz_min > 0)
+  float cz_min, cz_max, u_min, u_max, v_min, v_max;  // for the occlusion test (valid when cz_min > 0)
+  float d_far;  // set by occluded(): the largest depth the hull can project to (+inf when the pyramid was not consulted)
   __device__ __forceinline__ CullAccum()
-      : behind(true), left(true), right(true), top(true), bottom(true), cz_min(INFINITY), u_min(INFINITY),
-        u_max(-INFINITY), v_min(INFINITY), v_max(-INFINITY) {}
+      : behind(true), left(true), right(true), top(true), bottom(true), cz_min(INFINITY), cz_max(-INFINITY),
+        u_min(INFINITY), u_max(-INFINITY), v_min(INFINITY), v_max(-INFINITY), d_far(INFINITY) {}
   // PT: any struct with the cull fields of IntegrateParams (cull_z/gx/gy, im_w/h, mip_w/off, trunc_margin)
   template <class PT>
   __device__ __forceinline__ void add(float cx, float cy, float cz, const PT& P, const Intrinsics& K) {
     cz_min = fminf(cz_min, cz);
+    cz_max = fmaxf(cz_max, cz);
     const float inv = __fdividef(1.0f, cz);
     const float u = fmaf(K.fx * cx, inv, K.cx), v = fmaf(K.fy * cy, inv, K.cy);
     u_min = fminf(u_min, u); u_max = fmaxf(u_max, u);
@@ -681,8 +683,15 @@ struct CullAccum {
            (v_max <= (float)P.im_h - 2.5f);
   }
 
+  // Planning heuristic (never used for culling): after occluded() returned false, does the hull reach the +-trunc band
+  // of the FARTHEST surface it can project to?  Those tiles pay for exact evaluations on top of the classification.
   template <class PT>
-  __device__ __forceinline__ bool occluded(const PT& P, const float* __restrict__ mips) const {
+  __device__ __forceinline__ bool near_far_surface(const PT& P) const {
+    return d_far < 1e30f && cz_max + P.trunc_margin >= d_far;
+  }
+
+  template <class PT>
+  __device__ __forceinline__ bool occluded(const PT& P, const float* __restrict__ mips) {
     if (!(cz_min > P.cull_z + 1e-3f)) return false;
     const float fw = (float)P.im_w, fh = (float)P.im_h;
     if (!(u_min > -1e6f && u_max < 1e6f && v_min > -1e6f && v_max < 1e6f)) return false;
@@ -702,6 +711,7 @@ struct CullAccum {
     d_max = fmaxf(d_max, __ldg(m + ty0 * w_l + tx1));
     d_max = fmaxf(d_max, __ldg(m + ty1 * w_l + tx0));
     d_max = fmaxf(d_max, __ldg(m + ty1 * w_l + tx1));
+    d_far = d_max;
     return d_max + P.trunc_margin * 1.0001f + P.cull_z <= cz_min;
   }
 };
@@ -750,7 +760,7 @@ __device__ __forceinline__ void tile_frame_test(const IntegrateParams& P, const 
 template <class PT>
 __device__ __forceinline__ void box_frame_test(const PT& P, const Intrinsics& K, const FramePose& ps,
                                                const float* __restrict__ mips_f, int x_lo, int x_hi, int y_lo, int y_hi,
-                                               int z_lo, int z_hi, bool& keep, bool& inside) {
+                                               int z_lo, int z_hi, bool& keep, bool& inside, bool* near = nullptr) {
   CullAccum acc;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -763,6 +773,7 @@ __device__ __forceinline__ void box_frame_test(const PT& P, const Intrinsics& K,
   keep = !acc.culled();
   if (keep && P.cull_level >= 2 && mips_f != nullptr && P.trunc_margin > 0.0f) keep = !acc.occluded(P, mips_f);
   inside = keep && acc.interior(P);
+  if (near != nullptr) *near = keep && acc.near_far_surface(P);
 }
 
 }  // namespace

@@ -111,6 +111,7 @@ struct StreamLaunch {           // kernel parameter block (constant bank): what 
   int cull_level;
   float cull_z, cull_gx, cull_gy;
   int z_reverse;
+  int plan_beta;                      // work statistics: extra cost of a (tile, frame) pair that reaches a surface band
 };
 
 // Fills the geometry fields of L that follow from dim_x / dim_y / nz (nx_units, lx_shift, n_xt, n_yb, n_zg, n_btiles,

@@ -120,11 +120,13 @@ __global__ void __launch_bounds__(256) stream_mask_kernel(const __grid_constant_
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
           const int y_lo = yb_lo + w * rows_per_warp;
-          bool k = false, i = false;
+          bool k = false, i = false, nr = false;
           if (bk && y_lo < L.dim_y)
-            box_frame_test(L, K, ps, mips_f, x_lo, x_hi, y_lo, min(L.dim_y - 1, y_lo + rows_per_warp - 1), z_lo, z_hi, k, i);
+            box_frame_test(L, K, ps, mips_f, x_lo, x_hi, y_lo, min(L.dim_y - 1, y_lo + rows_per_warp - 1), z_lo, z_hi, k, i, &nr);
           keep_w[w] = __ballot_sync(0xffffffffu, k);
           in_w[w] = __ballot_sync(0xffffffffu, i);
+          // work statistics: a tile that reaches the band of the farthest surface behind it pays for exact evaluations
+          cost += (unsigned long long)L.plan_beta * (unsigned)__popc(__ballot_sync(0xffffffffu, nr));
         }
       }
     }
@@ -509,6 +511,11 @@ bool stream_prepare_geometry(StreamLaunch* L) {
   if (L->dim_x % VEC != 0 || !(L->trunc_margin > 0.0f) || (int64_t)L->im_w * L->im_h >= (1 << 22)) return false;
   if (L->chunk < 1 || L->chunk > kChunkMax) return false;
   if (L->epoch < 1) L->epoch = 8;
+  L->plan_beta = 3;   // (calibrated on the 1024^3 workload, profiles/README.md)
+  if (const char* e = getenv("TSDF_PLAN_BETA")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= 64) L->plan_beta = v;
+  }
   if (const char* e = getenv("TSDF_STREAM_EPOCH")) {   // tuning / A-B measurements
     const int v = atoi(e);
     if (v >= 1 && v <= kChunkMax) L->epoch = v;

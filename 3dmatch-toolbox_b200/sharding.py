@@ -253,32 +253,3 @@ def refine_plane_cost_piecewise(plane_cost, ranges, rank_ms, damping: float = 1.
         cost[a:b] *= r
     return cost
 
-
-def fit_plane_cost(prior, history, reg: float = 0.02) -> np.ndarray:
-    """Per-plane cost from ALL partitions measured so far.  `history`: list of (ranges, rank_ms).  The cuts of all
-    partitions split [0, dim_z) into intervals; inside an interval the cost keeps the prior's shape and gets one
-    scale factor, and the factors are the least-squares solution of `sum over the slab's intervals = measured rank
-    time` over every measurement (weakly regularised towards one common scale).  Planes that moved from one slab to
-    its neighbour between two partitions are thereby costed from the DIFFERENCE of the two measurements, which is what
-    locates a thin expensive band (the far wall) inside a slab."""
-    prior = np.maximum(np.asarray(prior, dtype=np.float64), 1e-300)
-    dim_z = len(prior)
-    cuts = sorted({0, dim_z} | {int(a) for ranges, _ in history for a, _ in ranges})
-    iv = list(zip(cuts[:-1], cuts[1:]))
-    P = np.array([prior[a:b].sum() for a, b in iv])
-    rows, rhs = [], []
-    for ranges, t in history:
-        for (a, b), tr in zip(ranges, t):
-            rows.append(np.array([P[j] if (a <= lo and hi <= b) else 0.0 for j, (lo, hi) in enumerate(iv)]))
-            rhs.append(float(tr))
-    A, y = np.array(rows), np.array(rhs)
-    s0 = y.sum() / max(A.sum(), 1e-300)
-    w = reg * np.sqrt(len(rows) / max(len(iv), 1))
-    A2 = np.vstack([A, w * np.diag(P)])
-    y2 = np.concatenate([y, w * P * s0])
-    sol, *_ = np.linalg.lstsq(A2, y2, rcond=None)
-    sol = np.clip(sol, 0.05 * s0, None)
-    out = prior.copy()
-    for (a, b), sj in zip(iv, sol):
-        out[a:b] *= sj
-    return out

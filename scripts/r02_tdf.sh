@@ -16,3 +16,4 @@ done
 echo "== warp phase B, epoch 2" >> gpurun_out/${tag}_warpb.log; TSDF_STREAM_WARPB=1 TSDF_STREAM_EPOCH=2 timeout 300 python scripts/tune_variants.py 256 32 0 >> gpurun_out/${tag}_warpb.log 2>&1
 echo "== warp phase B, epoch 16" >> gpurun_out/${tag}_warpb.log; TSDF_STREAM_WARPB=1 TSDF_STREAM_EPOCH=16 timeout 300 python scripts/tune_variants.py 256 32 0 >> gpurun_out/${tag}_warpb.log 2>&1
 cat gpurun_out/${tag}_warpb.log
+timeout 600 python scripts/plan_calibrate.py 256 > gpurun_out/${tag}_plan_calibrate.json 2> gpurun_out/${tag}_plan_calibrate.err; cat gpurun_out/${tag}_plan_calibrate.json; tail -3 gpurun_out/${tag}_plan_calibrate.err
