@@ -232,3 +232,35 @@ def test_surface_normals_vs_oracle(pkg, oracle, sequence):
     assert_bit_equal(nrm, ref, "surface normals")
     length = np.linalg.norm(nrm.astype(np.float64), axis=1)
     assert ((np.abs(length - 1) < 1e-6) | (length == 0)).all() and (length > 0).mean() > 0.9
+
+
+def test_config2_full_size_all_frames(pkg, oracle, sequence):
+    """BASELINE config 2 at full size (512^3, 6 mm voxels, 300 frames): per-frame (K = 1) == K = 32 through whole-volume
+    checksums, and oracle planes over ALL 300 frames (voxels are independent, so planes are exact samples)."""
+    import torch
+    frames = list(range(300))
+    depth, _, poses, K = sequence(frames)
+    dims, voxel, trunc = (512, 512, 512), 0.006, 0.03
+    n = dims[0] * dims[1] * dims[2]
+    depth_d = torch.from_numpy(depth).cuda()
+    sums = []
+    for batch in (32, 1):
+        t_dev = torch.empty(n, dtype=torch.float32, device="cuda")
+        w_dev = torch.empty(n, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        with pkg.Volume(dims, ORIGIN, voxel, trunc, K, max_batch=batch, ext_tsdf=t_dev, ext_weight=w_dev) as vol:
+            vol.reset()
+            vol.integrate_batch(depth_d, poses)
+            vol.synchronize()
+            n_pts = vol.extract_surface_count()
+        sums.append((int(t_dev.view(torch.int32).to(torch.int64).sum().item()), float(w_dev.double().sum().item()), n_pts))
+        if batch == 32:
+            tv, wv = t_dev.view(512, 512, 512), w_dev.view(512, 512, 512)
+            for z in (0, 7, 8, 100, 255, 256, 300, 400, 450, 480, 500, 511):
+                t_ref, w_ref = oracle.fuse(K, poses, depth, dims, ORIGIN, voxel, trunc, z_range=(z, z + 1))
+                assert_bit_equal(wv[z].cpu().numpy(), w_ref[0], f"weights plane {z}")
+                assert_bit_equal(tv[z].cpu().numpy(), t_ref[0], f"tsdf plane {z}")
+            assert float(w_dev.max().item()) > 250
+        del t_dev, w_dev
+    assert sums[0] == sums[1], f"K=32 vs K=1 checksums differ: {sums}"
+    assert sums[0][2] > 100000
