@@ -1,7 +1,7 @@
 """Host-side logic of bench.py and the slab balancing that can be checked without a GPU: the feedback balancing
-loop on a synthetic per-plane cost profile (frustum growth, an expensive surface band, nearly free planes behind
-it, a fixed per-rank overhead, noisy rank times), the nvidia-smi clock-sample parser, and the reported-baseline
-helper that must never raise."""
+loop on a synthetic per-plane cost profile (frustum growth, an expensive surface band the planner cannot see, nearly
+free planes behind it, a fixed per-rank overhead, noisy rank times), the nvidia-smi clock-sample parser, and the
+reported-baseline helper that must never raise."""
 import sys
 
 import numpy as np
@@ -20,56 +20,6 @@ def _truth(nz=1024):
     for zc, w, a in ((300, 40, 0.3), (520, 60, 0.5), (700, 50, 0.4)):
         c += a * np.exp(-0.5 * ((np.arange(nz) - zc) / w) ** 2) * (np.arange(nz) < wall)
     return c
-
-
-def test_feedback_balancing_converges(pkg):
-    """The loop of bench.py (measured plane cost -> equal-cost cuts -> damped refinement from rank times, best
-    measured partition kept) evens out eight ranks to a few percent within six steps."""
-    sh = pkg.sharding
-    truth = _truth()
-    world = 8
-    worst = 0.0
-    for seed in range(10):
-        rng = np.random.default_rng(seed)
-
-        def measure(ranges, noise=0.01):
-            t = np.array([truth[a:b].sum() for a, b in ranges]) * (55.0 * world / truth.sum()) + 4.0
-            return t * (1 + noise * rng.standard_normal(world))
-
-        # what measure_plane_cost() returns: 32-plane pieces, overhead-biased and noisy, interpolated per plane
-        edges = list(range(0, len(truth), 32)) + [len(truth)]
-        ms = np.array([truth[a:b].sum() for a, b in zip(edges[:-1], edges[1:])])
-        ms = (ms + 0.3 * ms.mean()) * (1 + 0.03 * rng.standard_normal(len(ms)))
-        centers = 0.5 * (np.array(edges[:-1]) + np.array(edges[1:]) - 1)
-        cost = np.maximum(np.interp(np.arange(len(truth)), centers, ms / np.diff(edges)), 1e-9)
-
-        ranges = sh.weighted_slab_ranges(cost, world)
-        best = None
-        for _ in range(6):
-            t = measure(ranges)
-            if best is None or t.max() < best[0]:
-                best = (t.max(), ranges)
-            if t.max() / t.mean() < 1.02:
-                break
-            cost = sh.refine_plane_cost(cost, ranges, t, damping=0.8)
-            new = sh.weighted_slab_ranges(cost, world)
-            if new == ranges:
-                break
-            ranges = new
-        t = measure(best[1], noise=0.0)
-        worst = max(worst, t.max() / t.mean())
-        assert best[1][0][0] == 0 and best[1][-1][1] == len(truth)
-    assert worst < 1.06, worst
-
-
-def test_refine_plane_cost_damping(pkg):
-    sh = pkg.sharding
-    cost = np.ones(64)
-    ranges = sh.weighted_slab_ranges(cost, 2)
-    full = sh.refine_plane_cost(cost, ranges, [1.0, 3.0])
-    damped = sh.refine_plane_cost(cost, ranges, [1.0, 3.0], damping=0.5)
-    # the slower slab's planes get more expensive, by less with damping
-    assert full[-1] > damped[-1] > 1.0 > damped[0] > full[0]
 
 
 def test_clock_sampler_parses_nvidia_smi_lines():

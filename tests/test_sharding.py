@@ -86,8 +86,8 @@ def test_split_slabs_equal_cost_at_group_granularity(pkg):
             assert sums.max() / sums.mean() < 1.0 + 2.5 * eff.max() / sums.mean(), (dim_z, world, sums)
     ranges = sh.split_groups(np.ones(128), 1024, 4)
     assert ranges == [(0, 256), (256, 512), (512, 768), (768, 1024)]
-    slow_last = sh.refine_group_cost(np.ones(128), ranges, [10.0, 10.0, 10.0, 16.0])
-    new = sh.split_groups(slow_last, 1024, 4)
+    slow_last = sh.refine_plane_cost_piecewise(sh.plane_cost_from_groups(np.ones(128), 1024), ranges, [10.0, 10.0, 10.0, 16.0])
+    new = sh.split_planes(slow_last, 4)
     assert new[-1][0] > ranges[-1][0]          # the slow last rank gets a shorter slab
     with pytest.raises(pkg.TsdfError):
         pkg.binding.split_slabs(np.ones(4, np.uint64), 32, 5)   # more slabs than groups
@@ -110,68 +110,3 @@ def test_slab_ranges_tile_the_volume(pkg):
     assert ranges[0][0] == 0 and ranges[-1][1] == 64 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
     costs = [np.linspace(1.0, 3.0, 64)[a:b].sum() for a, b in ranges]
     assert max(costs) / min(costs) < 1.15
-
-
-class _FakeVolume:
-    """Stands in for binding.Volume in measure_plane_cost(): its 'timer' reports a cost that is the sum of a known
-    per-plane density over the slab plus a fixed per-pass overhead (there is no GPU here)."""
-    density = np.concatenate([np.linspace(0.2, 1.0, 96), np.full(16, 6.0), np.full(16, 0.05)])   # 128 planes
-
-    def __init__(self, z0, z1):
-        self.z0, self.z1, self.frames = z0, z1, 0
-
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        return False
-
-    def integrate_batch(self, depth, poses, n_frames=None):
-        self.frames += int(n_frames)
-
-    def reset(self):
-        self.frames = 0
-
-    def synchronize(self):
-        pass
-
-    def timer_start(self):
-        self.frames = 0
-
-    def timer_stop(self):
-        return float(self.frames * (self.density[self.z0:self.z1].sum() + 0.3))
-
-
-def _cost_worker(rank, world, port, out_dir):
-    import sys
-    sys.path.insert(0, str(ROOT))
-    import __graft_entry__ as graft
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        sharding = graft.load_package().sharding
-        depth = torch.zeros((40, 4, 4))
-        poses = np.zeros((40, 16), np.float32)
-        cost = sharding.measure_plane_cost(_FakeVolume, depth, poses, 128, chunk=16, sample_batches=3, batch=8)
-        np.save(os.path.join(out_dir, f"cost{rank}.npy"), cost)
-    finally:
-        dist.destroy_process_group()
-
-
-def test_measured_plane_cost_is_shared_and_balances_gloo(tmp_path, pkg):
-    """measure_plane_cost(): the ranks time disjoint pieces, all-reduce, and derive the SAME per-plane cost; the
-    equal-cost partition built from it balances the true cost far better than equal heights."""
-    world = 2
-    mp.spawn(_cost_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    costs = [np.load(tmp_path / f"cost{r}.npy") for r in range(world)]
-    assert np.array_equal(costs[0], costs[1]) and costs[0].shape == (128,) and (costs[0] > 0).all()
-    sharding = pkg.sharding
-    truth = _FakeVolume.density
-
-    def spread(ranges):
-        t = np.array([truth[a:b].sum() for a, b in ranges])
-        return t.max() / t.mean()
-
-    balanced = spread(sharding.weighted_slab_ranges(costs[0], 4))
-    equal = spread([sharding.slab_range(128, r, 4) for r in range(4)])
-    assert balanced < 1.25 < equal, (balanced, equal)
