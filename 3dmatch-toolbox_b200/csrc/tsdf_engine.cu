@@ -500,10 +500,14 @@ int stream_stage_frames(tsdf_volume* v, StreamSlot& S, const Src* src, int ng, M
 template <typename Src>
 int stream_integrate(tsdf_volume* v, int n_frames, const Src* src, const float* cam2base, MemKind kind) {
   const int seg_cap = tsdf::kStreamMaxSegments * v->sl.chunk;
-  int group = (kind == MemKind::Device) ? kStreamGroupDevice : kStreamGroupHost;
-  if (group > seg_cap) group = seg_cap;
-  for (int g0 = 0; g0 < n_frames; g0 += group) {
-    const int ng = (n_frames - g0 < group) ? n_frames - g0 : group;
+  int group_max = (kind == MemKind::Device) ? kStreamGroupDevice : kStreamGroupHost;
+  if (group_max > seg_cap) group_max = seg_cap;
+  // host input: the first group is small so that the fusion starts after a short upload, the following ones grow (fewer
+  // launch tails); every group's upload overlaps the fusion of the previous one
+  int group = (kind == MemKind::Device) ? group_max : (group_max < 32 ? group_max : 32);
+  for (int g0 = 0, ng = 0; g0 < n_frames; g0 += ng) {
+    ng = (n_frames - g0 < group) ? n_frames - g0 : group;
+    group = (group * 3 < group_max) ? group * 3 : group_max;
     // device input is staged and fused in stream order, so one slot suffices; host input alternates two slots so
     // that the copy of group g + 1 overlaps the fusion of group g
     StreamSlot& S = v->ss[(kind == MemKind::Device) ? 0 : (int)(v->stream_group++ % kStreamSlots)];

@@ -25,7 +25,7 @@ constexpr int kMaxSub = 4;  // concurrent sub-slab streams per handle
 // ---- stream engine (tsdf_stream_kernels.cu) ----
 constexpr int kStreamSlots = 2;
 constexpr int kStreamGroupDevice = 1024;  // frames per persistent launch when the input is device-resident
-constexpr int kStreamGroupHost = 128;     // ... when it is host memory (double-buffered against the H2D copies)
+constexpr int kStreamGroupHost = 256;     // ... at most, when it is host memory (double-buffered against the H2D copies)
 constexpr int kCounterWords = 2 * tsdf::kStreamMaxSegments + 8;  // item_count[], seg_begin[], ticket
 
 // Buffers of one group of frames in flight: the engine's own sanitized copy of the frames, their depth pyramids and
