@@ -201,14 +201,17 @@ def test_plan_z_cost_matches_engine_statistics_and_balances(pkg, sequence):
     cost = pkg.plan_z_cost(dims, ORIGIN, voxel, trunc, K, depth, poses)
     cost_dev = pkg.plan_z_cost(dims, ORIGIN, voxel, trunc, K, torch.from_numpy(mm.view(np.int16)).cuda(), poses)
     assert cost.shape == (32,) and cost.sum() > 0 and np.array_equal(cost, cost_dev)
+    # (device input: the engine fuses the 64 frames as ONE group, so its cull margins -- derived from the group's poses --
+    #  are the planner's; host input is cut into several groups with slightly different conservative margins)
+    depth_d = torch.from_numpy(depth).cuda()
     with pkg.Volume(dims, ORIGIN, voxel, trunc, K) as vol:
-        vol.integrate_batch(depth, poses)
+        vol.integrate_batch(depth_d, poses)
         assert np.array_equal(vol.z_cost(), cost)
     ranges = pkg.sharding.split_groups(cost, dims[2], 4)
     part = []
     for a, b in ranges:
         with pkg.Volume(dims, ORIGIN, voxel, trunc, K, z_range=(a, b)) as vol:
-            vol.integrate_batch(depth, poses)
+            vol.integrate_batch(depth_d, poses)
             part.append(int(vol.z_cost().sum()))
     assert sum(part) == int(cost.sum())           # slabs cut at multiples of 8 planes see exactly the same tiles
     eq = [int(cost[a // 8:b // 8].sum()) for a, b in [(0, 64), (64, 128), (128, 192), (192, 256)]]
