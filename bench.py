@@ -72,6 +72,10 @@ def use_all_host_threads():
     """The reference arms run OpenMP code: torch.distributed.run exports OMP_NUM_THREADS=1 to its children, so the
     thread count is set explicitly (environment for libraries not loaded yet, omp_set_num_threads for libgomp)."""
     n = os.cpu_count() or 1
+    try:   # NCCL / the launcher may have narrowed this process to the cores next to its GPU: OpenMP workers inherit the mask
+        os.sched_setaffinity(0, range(n))
+    except (AttributeError, OSError):
+        pass
     os.environ["OMP_NUM_THREADS"] = str(n)
     try:
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
