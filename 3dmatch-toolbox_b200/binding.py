@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "tsdf_point_cloud_to_tdf", "tsdf_integrate_multi", "tsdf_plan_z_cost", "tsdf_get_z_cost", "tsdf_split_slabs",
     "tsdf_sharded_create", "tsdf_sharded_destroy", "tsdf_sharded_reset", "tsdf_sharded_synchronize",
     "tsdf_sharded_integrate_batch", "tsdf_sharded_extract_surface", "tsdf_sharded_copy_surface", "tsdf_sharded_write_bin",
-    "tsdf_sharded_slab", "tsdf_copy_surface_normals",
+    "tsdf_sharded_slab", "tsdf_copy_surface_normals", "tsdf_selftest_packed",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library(validation: bool = False) -> C.CDLL:
         "tsdf_sharded_slab": [vp, C.c_int32, C.POINTER(vp), i64p, i64p, C.POINTER(C.c_int32)],
         "tsdf_device_count": [C.POINTER(C.c_int32)],
         "tsdf_selftest_rounding": [C.c_int32, i64p],
+        "tsdf_selftest_packed": [C.c_int32, i64p],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -338,6 +339,12 @@ def integrate_multi(volumes, depth_list, pose_list, n_frames=None):
 def device_count() -> int:
     n = C.c_int32(0)
     _check(load_library().tsdf_device_count(C.byref(n)), "tsdf_device_count")
+    return n.value
+
+
+def selftest_packed(device=0) -> int:
+    n = C.c_int64(-1)
+    _check(load_library().tsdf_selftest_packed(device, C.byref(n)), "tsdf_selftest_packed")
     return n.value
 
 

@@ -1217,6 +1217,21 @@ int tsdf_split_slabs(const uint64_t* cost, int32_t n_groups, int64_t dim_z, int3
   return TSDF_OK;
 }
 
+int tsdf_selftest_packed(int32_t device, int64_t* mismatches) {
+  if (!mismatches) return set_err(TSDF_ERR_ARG, "mismatches is NULL");
+  CK(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc(&d, sizeof *d));
+  CK(cudaMemset(d, 0, sizeof *d));
+  cudaError_t e = tsdf::launch_selftest_packed(d, 0);
+  unsigned long long h = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CK(e);
+  *mismatches = (int64_t)h;
+  return TSDF_OK;
+}
+
 int tsdf_selftest_rounding(int32_t device, int64_t* mismatches) {
   if (!mismatches) return set_err(TSDF_ERR_ARG, "mismatches is NULL");
   CK(cudaSetDevice(device));

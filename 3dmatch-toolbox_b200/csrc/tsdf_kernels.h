@@ -158,6 +158,7 @@ cudaError_t launch_extract_emit(const ExtractParams& p, const unsigned long long
 cudaError_t launch_surface_normals(const ExtractParams& p, int64_t nz, const long long* voxel_index, int64_t n,
                                    float* normals, cudaStream_t s);
 cudaError_t launch_selftest_rounding(unsigned long long* mismatches, cudaStream_t s);
+cudaError_t launch_selftest_packed(unsigned long long* mismatches, cudaStream_t s);   // tsdf_stream_kernels.cu
 // tdf_kernels.cu: scratch = compute_tdf_scratch_bytes() bytes of device memory (two intermediate grids, 8 or 16 bit)
 size_t compute_tdf_scratch_bytes(int dim_x, int dim_y, int dim_z, int radius);
 cudaError_t launch_compute_tdf(const float* occ, float* tdf, void* scratch, int dim_x, int dim_y, int dim_z,

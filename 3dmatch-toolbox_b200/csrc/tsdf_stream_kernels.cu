@@ -39,22 +39,28 @@ constexpr int VEC = 4, ZT = 8;
 constexpr int kWarps = kBlockThreads / 32;
 constexpr int kRecCap = kBlockThreads * VEC * ZT;  // every voxel of a block tile becomes sticky at most once per item
 
-// Exactly rounded packed fp32 operations with a scalar (broadcast) second operand.  The explicit .rn forms are never
-// contracted into a fused multiply-add, so mul2s followed by add2s is two roundings, like __fmul_rn / __fadd_rn.
+// Packed fp32 add / sub with a scalar (broadcast) second operand: one IEEE rounding per lane.
+// NOTE: ptxas (12.9) contracts a packed multiply whose only use is a packed add into FFMA2 -- even with explicit .rn
+// modifiers, even with --fmad=false, even when the multiply is written as fma(a, b, -0) -- which would turn the
+// reference's two roundings of (M0*t0 + M4*t1) into one.  Products that feed an add are therefore formed with the
+// scalar mul.rn.f32 (never contracted) and only the add is packed; tsdf_selftest_packed() pins the result bit for bit
+// against the scalar intrinsics.
 __device__ __forceinline__ f32x2_t sub2s(f32x2_t a, float s) {
   f32x2_t r;
   asm("{\n\t.reg .b64 b;\n\tmov.b64 b, {%2, %2};\n\tsub.rn.f32x2 %0, %1, b;\n\t}" : "=l"(r) : "l"(a), "f"(s));
-  return r;
-}
-__device__ __forceinline__ f32x2_t mul2s(f32x2_t a, float s) {
-  f32x2_t r;
-  asm("{\n\t.reg .b64 b;\n\tmov.b64 b, {%2, %2};\n\tmul.rn.f32x2 %0, %1, b;\n\t}" : "=l"(r) : "l"(a), "f"(s));
   return r;
 }
 __device__ __forceinline__ f32x2_t add2s(f32x2_t a, float s) {
   f32x2_t r;
   asm("{\n\t.reg .b64 b;\n\tmov.b64 b, {%2, %2};\n\tadd.rn.f32x2 %0, %1, b;\n\t}" : "=l"(r) : "l"(a), "f"(s));
   return r;
+}
+
+// demo.cu:35-41 for two x-adjacent voxels: fl(fl(m * t0) + y) with t0 = fl(bx - tx), one rounding per operation.
+__device__ __forceinline__ f32x2_t setup_pair(f32x2_t t0, float m, float y) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(t0));
+  return add2s(pack2(__fmul_rn(lo, m), __fmul_rn(hi, m)), y);
 }
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -195,16 +201,16 @@ __global__ void __launch_bounds__(kStreamMaxSegments) stream_segment_kernel(cons
 // ------------------------------------------------------------------------------------------------
 // DIAG (validation library only, results are NOT valid): 1 = no TSDF / weight traffic at all, so that every L2 read of
 // the launch is a depth gather (cache evidence in profiles/); 2 = depth gathers with an L2 evict_last cache hint (A/B).
-// WARPB: phase B per WARP (each warp evaluates the sticky voxels of its own tile right after its own phase A; no block
-// barrier inside an item) instead of pooled over the block (full lanes, one barrier per epoch).
-template <int MINB, int DIAG = 0, bool WARPB = false>
+// G: phase B is pooled over 256 / G threads: G = 1 the whole block (fullest lanes, one block barrier per epoch), G = 2 / 4
+// half / quarter blocks synchronised by named barriers (fewer warps wait for each other), G = 8 per warp (no barrier at
+// all, emptiest lanes).
+template <int MINB, int DIAG = 0, int G = 1>
 __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(const __grid_constant__ StreamLaunch L) {
   __shared__ float4 s_ztab[kChunkMax * ZT];        // plane products M8*t2 of every (frame, plane) of the item
   __shared__ float4 s_pose[kChunkMax * 3];         // (m0 m1 m2 tx) (m4 m5 m6 ty) (m8 m9 m10 tz) per frame
   __shared__ unsigned s_pend[ZT][kBlockThreads];   // byte j of [k][t]: pending free-space updates of voxel (j, k) of thread t
   __shared__ unsigned s_wmask[kWarps];
-  __shared__ unsigned s_rec_count[3];              // record counters, rotating over the epochs
-  __shared__ unsigned s_wcount[kWarps];            // WARPB: record counter of every warp
+  __shared__ unsigned s_rec_count[G][3];           // record counters of every group, rotating over the epochs
   __shared__ unsigned s_hdr[4];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -267,8 +273,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
     const uint2 wm2 = __ldg(J.masks + ((int64_t)chunk * L.n_btiles + btile) * kWarps + warp);
     const unsigned frame_mask = wm2.x, interior_mask = wm2.y;
     if (lane == 0) s_wmask[warp] = frame_mask;
-    if (threadIdx.x == 0) s_rec_count[0] = s_rec_count[1] = s_rec_count[2] = 0u;
-    if (lane == 0) s_wcount[warp] = 0u;
+    if (threadIdx.x < 3 * G) (&s_rec_count[0][0])[threadIdx.x] = 0u;
     for (int e = threadIdx.x; e < nf * ZT; e += kBlockThreads) {
       const int f = e / ZT, k = e - f * ZT;
       const FramePose ps = poses[f];
@@ -299,24 +304,30 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
       bx2[h] = pack2(__fadd_rn(L.ox, __fmul_rn((float)(xu * VEC + 2 * h), L.voxel_size)),
                      __fadd_rn(L.ox, __fmul_rn((float)(xu * VEC + 2 * h + 1), L.voxel_size)));
 
-    unsigned block_mask = 0u;
+    constexpr int kWarpsPerGroup = kWarps / G, kGroupThreads = kBlockThreads / G, kGroupRecCap = kRecCap / G;
+    const int grp = warp / kWarpsPerGroup;
+    auto group_barrier = [&]() {
+      if constexpr (G == 1) __syncthreads();
+      else if constexpr (G == kWarps) __syncwarp();
+      else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kGroupThreads) : "memory");
+    };
+    unsigned group_mask = 0u;
 #pragma unroll
-    for (int w8 = 0; w8 < kWarps; ++w8) block_mask |= s_wmask[w8];
+    for (int w8 = 0; w8 < kWarpsPerGroup; ++w8) group_mask |= s_wmask[grp * kWarpsPerGroup + w8];
 
     // The chunk is walked in EPOCHS of L.epoch frames: phase A (classification, per warp) of the epoch's frames, then
-    // phase B (exact evaluation of the voxels that became sticky in this epoch, whole block), then the sticky marks are
-    // dropped.  A voxel flagged only because its pixel rounding was within the margin at one frame therefore costs at
-    // most one epoch of exact evaluations, while voxels inside the +-trunc band are simply flagged again.
+    // phase B (exact evaluation of the voxels that became sticky in this epoch, pooled over the group), then the sticky
+    // marks are dropped.  A voxel flagged only because its pixel rounding was within the margin at one frame therefore
+    // costs at most one epoch of exact evaluations, while voxels inside the +-trunc band are simply flagged again.
     // One barrier per epoch: the record lists alternate between two buffers and the counters rotate over three words,
     // so a warp that has finished its share of phase B goes straight on to the next epoch's phase A.
     unsigned n_epoch = 0u;
     for (int e0 = 0; e0 < nf; e0 += L.epoch) {
       const unsigned epoch_bits = ((L.epoch >= 32) ? 0xffffffffu : ((1u << L.epoch) - 1u)) << e0;
-      if (((WARPB ? frame_mask : block_mask) & epoch_bits) == 0u) continue;  // block-uniform (WARPB: warp-uniform)
+      if ((group_mask & epoch_bits) == 0u) continue;  // group-uniform
       const unsigned slot = n_epoch % 3u;
-      // block mode: two lists alternating over the epochs; WARPB: one list of 1024 records (= voxels of a warp tile) per warp
-      unsigned* const rec = WARPB ? rec_base + warp * (kRecCap / kWarps) : rec_base + (n_epoch & 1u) * kRecCap;
-      unsigned* const counter = WARPB ? &s_wcount[warp] : &s_rec_count[slot];
+      unsigned* const rec = rec_base + grp * (2 * kGroupRecCap) + (n_epoch & 1u) * kGroupRecCap;
+      unsigned* const counter = &s_rec_count[grp][slot];
       ++n_epoch;
 
       // ---------------- phase A: classification, per warp ----------------
@@ -324,8 +335,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
       for (unsigned fm = frame_mask & epoch_bits; fm != 0u; fm &= fm - 1u) {
         const int f = __ffs(fm) - 1;
         const float4 p0 = s_pose[f * 3 + 0], p1 = s_pose[f * 3 + 1];
-        // demo.cu:35-41: (M0*t0 + M4*t1) per x with the reference's operations (one rounding each; the packed
-        // mul.rn / add.rn forms are exactly rounded per lane and never contracted); the M8*t2 part comes from s_ztab
+        // demo.cu:35-41: (M0*t0 + M4*t1) per x with the reference's operations, one rounding each (setup_pair); the M8*t2
+        // part comes from s_ztab
         const float t1 = __fsub_rn(base_y, p1.w);
         const float yx = __fmul_rn(p1.x, t1), yy = __fmul_rn(p1.y, t1), yz = __fmul_rn(p1.z, t1);
         unsigned exact = 0u;  // bit k*VEC + j: the observation of this frame is not certain
@@ -334,9 +345,9 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const f32x2_t t0 = sub2s(bx2[h], p0.w);
-            sx2[h] = add2s(mul2s(t0, p0.x), yx);
-            sy2[h] = add2s(mul2s(t0, p0.y), yy);
-            sz2[h] = add2s(mul2s(t0, p0.z), yz);
+            sx2[h] = setup_pair(t0, p0.x, yx);
+            sy2[h] = setup_pair(t0, p0.y, yy);
+            sz2[h] = setup_pair(t0, p0.z, yz);
           }
           // gather base biased by the bit pattern of the rint magic (see voxel_classify_pair)
           const char* depth_biased =
@@ -406,14 +417,14 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
           }
         }
       }
-      if constexpr (WARPB) __syncwarp(); else __syncthreads();  // the epoch's records are complete
+      group_barrier();  // the epoch's records are complete
 
       // ---------------- phase B: sticky voxels, one record per thread, frames in ascending order ----------------
       const unsigned n_rec = *counter;
-      // block mode: the counter of the epoch after the next one was last read in the previous epoch's phase B, i.e.
-      // before this barrier, and is first written after the next epoch's barrier
-      if (!WARPB && threadIdx.x == 0) s_rec_count[(slot + 2u) % 3u] = 0u;
-      for (unsigned base = WARPB ? 0u : (unsigned)warp * 32u; base < n_rec; base += (WARPB ? 32u : (unsigned)kBlockThreads)) {  // warp-uniform trip count
+      // the counter of the epoch after the next one was last read in the previous epoch's phase B, i.e. before this
+      // barrier, and is first written after the next epoch's barrier
+      if ((threadIdx.x & (kGroupThreads - 1)) == 0) s_rec_count[grp][(slot + 2u) % 3u] = 0u;
+      for (unsigned base = (unsigned)(warp - grp * kWarpsPerGroup) * 32u; base < n_rec; base += (unsigned)kGroupThreads) {  // warp-uniform trip count
         const unsigned i = base + (unsigned)lane;
         const bool valid = i < n_rec;
         unsigned wm = 0u, c = 0u;
@@ -466,14 +477,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
           __stcg(weight + idx, w);
         }
       }
-      if constexpr (WARPB) {   // the warp's list is free again
-        __syncwarp();
-        if (lane == 0) *counter = 0u;
-        __syncwarp();
-      }
     }
-    // every phase B store precedes the write-back's loads (WARPB: both touch only this warp's own voxels)
-    if constexpr (WARPB) __syncwarp(); else __syncthreads();
+    group_barrier();  // every phase B store of the group precedes the write-back's loads
 
     // ---------------- write-back of the pending counts (certain free-space observations), coalesced ----------------
     // (after the last phase B: the float4 rows are re-read here, so they carry phase B's stores)
@@ -501,6 +506,32 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
     __syncthreads();
     if (threadIdx.x == 0) st_release(J.progress + btile, (unsigned)chunk + 1u);
   }
+}
+
+// Self-test of the packed set-up arithmetic against the scalar round-to-nearest intrinsics on pseudo-random operands
+// (all magnitudes the path sees, signs mixed): counts lanes whose bits differ.
+__global__ void __launch_bounds__(256) selftest_packed_kernel(unsigned long long* __restrict__ mismatches, unsigned n_per_thread) {
+  unsigned long long state = 0x9E3779B97F4A7C15ull * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1ull);
+  auto next = [&]() {   // splitmix64 -> float in (-4, 4) with a random exponent spread
+    state += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = state;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);           // [0, 1)
+    const float scale = __uint_as_float(((unsigned)((z >> 8) & 7u) + 122u) << 23);  // 2^-5 .. 2^2
+    return ((z & 1ull) ? -u : u) * scale;
+  };
+  unsigned long long bad = 0;
+  for (unsigned i = 0; i < n_per_thread; ++i) {
+    const float b0 = next(), b1 = next(), tx = next(), m = next(), y = next();
+    const f32x2_t got = setup_pair(sub2s(pack2(b0, b1), tx), m, y);
+    float g0, g1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(g0), "=f"(g1) : "l"(got));
+    const float r0 = __fadd_rn(__fmul_rn(__fsub_rn(b0, tx), m), y), r1 = __fadd_rn(__fmul_rn(__fsub_rn(b1, tx), m), y);
+    bad += (__float_as_uint(g0) != __float_as_uint(r0)) + (__float_as_uint(g1) != __float_as_uint(r1));
+  }
+  if (bad) atomicAdd(mismatches, bad);
 }
 
 int g_resident_blocks[64] = {};
@@ -582,6 +613,11 @@ cudaError_t launch_stream_masks(const StreamLaunch& L, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_selftest_packed(unsigned long long* mismatches, cudaStream_t s) {
+  selftest_packed_kernel<<<148 * 8, 256, 0, s>>>(mismatches, 4096);   // 2.5e9 lanes
+  return cudaGetLastError();
+}
+
 cudaError_t launch_stream_cost(const StreamLaunch& L, cudaStream_t s) {
   if (L.n_jobs < 1) return cudaErrorInvalidValue;
   const int64_t blocks = ((int64_t)L.n_jobs * L.n_btiles * 32 + 255) / 256;
@@ -599,9 +635,11 @@ cudaError_t launch_stream_integrate(const StreamLaunch& L, int n_blocks, cudaStr
     if (v == 2) { stream_integrate_kernel<5, 2><<<n_blocks, kBlockThreads, 0, s>>>(L); return cudaGetLastError(); }
   }
 #endif
-  static const bool warpb = getenv("TSDF_STREAM_WARPB") && atoi(getenv("TSDF_STREAM_WARPB")) == 1;
-  if (warpb) {   // A/B switch: phase B per warp instead of pooled over the block
-    stream_integrate_kernel<5, 0, true><<<n_blocks, kBlockThreads, 0, s>>>(L);
+  static const int groups = getenv("TSDF_STREAM_GROUPS") ? atoi(getenv("TSDF_STREAM_GROUPS")) : 1;
+  if (groups == 2 || groups == 4 || groups == 8) {   // A/B switch: phase B pooled over 128 / 64 / 32 threads
+    if (groups == 2) stream_integrate_kernel<5, 0, 2><<<n_blocks, kBlockThreads, 0, s>>>(L);
+    else if (groups == 4) stream_integrate_kernel<5, 0, 4><<<n_blocks, kBlockThreads, 0, s>>>(L);
+    else stream_integrate_kernel<5, 0, 8><<<n_blocks, kBlockThreads, 0, s>>>(L);
     return cudaGetLastError();
   }
   switch (stream_min_blocks()) {

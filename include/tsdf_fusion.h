@@ -232,6 +232,9 @@ int tsdf_device_count(int32_t *count);
 /* Device self-test of the pixel rounding helper against roundf() + the reference bounds test
  * (demo.cu:46-49) over all 2^32 float bit patterns; *mismatches receives the count (0 expected). */
 int tsdf_selftest_rounding(int32_t device, int64_t *mismatches);
+/* Device self-test of the packed (f32x2) set-up arithmetic of the fusion kernel against the scalar round-to-nearest
+ * intrinsics (one IEEE rounding per operation of demo.cu:35-41) on 2.5e9 pseudo-random lanes; 0 expected. */
+int tsdf_selftest_packed(int32_t device, int64_t *mismatches);
 
 #ifdef __cplusplus
 }

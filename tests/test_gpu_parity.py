@@ -19,6 +19,13 @@ def fuse_gpu(pkg, K, poses, depth, dims, origin, voxel, trunc, **kw):
     return t, w, pts
 
 
+def test_packed_setup_arithmetic_is_two_roundings(pkg):
+    """The fusion kernel's packed (f32x2) set-up of demo.cu:35-41 against the scalar round-to-nearest intrinsics on
+    2.5e9 pseudo-random lanes: ptxas contracts a packed multiply feeding a packed add into FFMA2 (one rounding) whatever
+    the rounding modifiers say, so the products are formed with scalar mul.rn -- this test is what pins that."""
+    assert pkg.binding.selftest_packed(0) == 0
+
+
 def test_rounding_helper_all_float_bit_patterns(pkg):
     """round_pixel() == roundf() + the reference bounds test (demo.cu:46-49) for all 2^32 floats."""
     assert pkg.binding.selftest_rounding(0) == 0
