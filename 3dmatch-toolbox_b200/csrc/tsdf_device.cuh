@@ -39,9 +39,9 @@ constexpr float kNoObservation = 2.0f;
 // marks a NaN pixel.  The reference does NOT reject NaN (demo.cu:53: both comparisons are false; :57 likewise) and
 // ends with fmin(1.0f, NaN) = 1.0f (demo.cu:62), i.e. a dist = 1 observation.
 template <bool BAND_SHORTCUT, bool SANITIZED = false>
-__device__ __noinline__ float voxel_observation_exact(float cam_x, float cam_y, float cam_z, float fx, float fy,
-                                                      float cx, float cy, const float* __restrict__ depth,
-                                                      int im_w, int im_h, float trunc_margin) {
+__device__ __forceinline__ float voxel_observation_exact_inline(float cam_x, float cam_y, float cam_z, float fx, float fy,
+                                                                float cx, float cy, const float* __restrict__ depth,
+                                                                int im_w, int im_h, float trunc_margin) {
   if (cam_z <= 0.0f) return kNoObservation;                          // demo.cu:43
   const float qx = __fdiv_rn(cam_x, cam_z);
   const float qy = __fdiv_rn(cam_y, cam_z);
@@ -64,6 +64,15 @@ __device__ __noinline__ float voxel_observation_exact(float cam_x, float cam_y, 
   const float diff = __fmul_rn(e, ray);
   if (diff <= -trunc_margin) return kNoObservation;                  // demo.cu:57
   return fminf(1.0f, __fdiv_rn(diff, trunc_margin));                 // demo.cu:62
+}
+
+// Out-of-line form for the kernels that call it from many places (tsdf_kernels.cu).
+template <bool BAND_SHORTCUT, bool SANITIZED = false>
+__device__ __noinline__ float voxel_observation_exact(float cam_x, float cam_y, float cam_z, float fx, float fy,
+                                                      float cx, float cy, const float* __restrict__ depth,
+                                                      int im_w, int im_h, float trunc_margin) {
+  return voxel_observation_exact_inline<BAND_SHORTCUT, SANITIZED>(cam_x, cam_y, cam_z, fx, fy, cx, cy, depth, im_w, im_h,
+                                                                   trunc_margin);
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {
