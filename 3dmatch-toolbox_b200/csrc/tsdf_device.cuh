@@ -41,7 +41,10 @@ constexpr float kNoObservation = 2.0f;
 template <bool BAND_SHORTCUT, bool SANITIZED = false>
 __device__ __forceinline__ float voxel_observation_exact_inline(float cam_x, float cam_y, float cam_z, float fx, float fy,
                                                                 float cx, float cy, const float* __restrict__ depth,
-                                                                int im_w, int im_h, float trunc_margin) {
+                                                                int im_w, int im_h, float trunc_margin,
+                                                                unsigned frame_offset = 0u) {
+  // frame_offset: element offset of the frame inside `depth` (a 32-bit sum with the pixel index instead of a 64-bit
+  // pointer per frame)
   if (cam_z <= 0.0f) return kNoObservation;                          // demo.cu:43
   const float qx = __fdiv_rn(cam_x, cam_z);
   const float qy = __fdiv_rn(cam_y, cam_z);
@@ -51,7 +54,7 @@ __device__ __forceinline__ float voxel_observation_exact_inline(float cam_x, flo
   const bool in_x = round_pixel(u, (float)im_w, px);
   const bool in_y = round_pixel(v, (float)im_h, py);
   if (!(in_x && in_y)) return kNoObservation;                        // demo.cu:48
-  const float d = __ldg(depth + (py * im_w + px));                   // demo.cu:51
+  const float d = __ldg(depth + (frame_offset + (unsigned)(py * im_w + px)));   // demo.cu:51
   if (SANITIZED && d == INFINITY) return 1.0f;                       // NaN pixel: demo.cu:53-62 yield dist = 1
   if (d <= 0.0f || d > 6.0f) return kNoObservation;                  // demo.cu:53
   const float e = __fsub_rn(d, cam_z);

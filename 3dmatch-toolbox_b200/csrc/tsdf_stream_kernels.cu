@@ -463,9 +463,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
             const float cam_x = __fadd_rn(__fadd_rn(__fmul_rn(p0.x, t0), __fmul_rn(p1.x, t1)), __fmul_rn(p2.x, t2));
             const float cam_y = __fadd_rn(__fadd_rn(__fmul_rn(p0.y, t0), __fmul_rn(p1.y, t1)), __fmul_rn(p2.y, t2));
             const float cam_z = __fadd_rn(__fadd_rn(__fmul_rn(p0.z, t0), __fmul_rn(p1.z, t1)), __fmul_rn(p2.z, t2));
-            const float dj = voxel_observation_exact_inline<true, true>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy,
-                                                                        depth0 + (int64_t)f * L.frame_stride, L.im_w,
-                                                                        L.im_h, L.trunc_margin);
+            // (a chunk's frames span < 2^31 elements: 32-bit frame offset)
+            const float dj = voxel_observation_exact_inline<true, true>(cam_x, cam_y, cam_z, K.fx, K.fy, K.cx, K.cy, depth0,
+                                                                        L.im_w, L.im_h, L.trunc_margin,
+                                                                        (unsigned)f * (unsigned)L.frame_stride);
             if (dj != kNoObservation) {
               voxel_update(t, w, dj);  // demo.cu:63-66
               changed = true;
