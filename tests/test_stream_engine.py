@@ -267,3 +267,36 @@ def test_config2_full_size_all_frames(pkg, oracle, sequence):
         del t_dev, w_dev
     assert sums[0] == sums[1], f"K=32 vs K=1 checksums differ: {sums}"
     assert sums[0][2] > 100000
+
+
+def test_stream_every_voxel_in_the_band(pkg, oracle, sequence):
+    """A truncation margin far larger than the scene: every voxel with a valid pixel is inside the band at every frame,
+    so every voxel of every tile becomes a sticky record in every epoch (the record lists run at full capacity, 8192 per
+    block) and the whole fusion goes through phase B."""
+    frames = [(13 * i) % 700 for i in range(45)]
+    depth, _, poses, K = sequence(frames)
+    dims, voxel, trunc = (64, 64, 24), 0.045, 12.0
+    t_ref, w_ref = oracle.fuse(K, poses, depth, dims, ORIGIN, voxel, trunc)
+    assert (np.abs(t_ref[w_ref > 0]) < 1).mean() > 0.95
+    for chunk in (32, 7):
+        t, w, _ = fuse_gpu(pkg, K, poses, depth, dims, ORIGIN, voxel, trunc, max_batch=chunk)
+        assert_bit_equal(w, w_ref, f"weights chunk={chunk}")
+        assert_bit_equal(t, t_ref, f"tsdf chunk={chunk}")
+
+
+def test_stream_more_frames_than_one_group(pkg, oracle, sequence):
+    """2200 frames in one call: device input is fused in groups of 1024 frames (three persistent launches), host input
+    in groups of 32, 96, 256, ... ; with K = 1 a group holds 1024 one-frame chunks (the segment table at its limit)."""
+    import torch
+    base = [(9 * i) % 500 for i in range(50)]
+    depth, _, poses, K = sequence(base)
+    reps = 44
+    depth_all = np.tile(depth, (reps, 1, 1))
+    poses_all = np.tile(poses, (reps, 1))
+    dims, voxel, trunc = (32, 32, 16), 0.09, 0.45
+    t_ref, w_ref = oracle.fuse(K, poses_all, depth_all, dims, ORIGIN, voxel, trunc)
+    assert w_ref.max() > 1000
+    for src, chunk in ((torch.from_numpy(depth_all).cuda(), 0), (depth_all, 0), (torch.from_numpy(depth_all).cuda(), 1)):
+        t, w, _ = fuse_gpu(pkg, K, poses_all, src, dims, ORIGIN, voxel, trunc, max_batch=chunk)
+        assert_bit_equal(w, w_ref, f"weights chunk={chunk}")
+        assert_bit_equal(t, t_ref, f"tsdf chunk={chunk}")
