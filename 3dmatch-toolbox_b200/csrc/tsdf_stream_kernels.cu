@@ -576,29 +576,48 @@ bool stream_prepare_geometry(StreamLaunch* L) {
   return true;
 }
 
-// Resident blocks per SM the kernel is compiled for: 6 (40 registers), 5 (48) or 4 (64).  TSDF_STREAM_MINB in the
-// environment overrides the default for A/B measurements.
-int stream_min_blocks() {
-  static int minb = 0;
-  if (minb == 0) {
-    minb = 5;
-    if (const char* e = getenv("TSDF_STREAM_MINB")) {
-      const int v = atoi(e);
-      if (v == 4 || v == 5 || v == 6) minb = v;
-    }
+// The shipped library carries ONE instantiation: 5 resident blocks per SM (48 registers), phase B pooled over the
+// block.  The validation library additionally carries the variants measured in profiles/README.md, selected through the
+// environment: TSDF_STREAM_MINB = 4 | 6 (64 / 40 registers), TSDF_STREAM_GROUPS = 2 | 4 | 8 (phase B pooled over
+// 128 / 64 / 32 threads), TSDF_STREAM_DIAG = 1 | 2 (see stream_integrate_kernel).
+struct StreamVariant { int minb, groups, diag; };
+
+StreamVariant stream_variant() {
+  static StreamVariant v = {0, 1, 0};
+  if (v.minb == 0) {
+    v.minb = 5;
+#ifdef TSDF_VALIDATION
+    if (const char* e = getenv("TSDF_STREAM_MINB")) { const int x = atoi(e); if (x == 4 || x == 6) v.minb = x; }
+    if (const char* e = getenv("TSDF_STREAM_GROUPS")) { const int x = atoi(e); if (x == 2 || x == 4 || x == 8) v.groups = x; }
+    if (const char* e = getenv("TSDF_STREAM_DIAG")) { const int x = atoi(e); if (x == 1 || x == 2) v.diag = x; }
+#endif
   }
-  return minb;
+  return v;
+}
+
+using StreamKernel = void (*)(const StreamLaunch);
+
+StreamKernel stream_kernel() {
+#ifdef TSDF_VALIDATION
+  const StreamVariant v = stream_variant();
+  if (v.diag == 1) return stream_integrate_kernel<5, 1>;
+  if (v.diag == 2) return stream_integrate_kernel<5, 2>;
+  if (v.groups == 2) return stream_integrate_kernel<5, 0, 2>;
+  if (v.groups == 4) return stream_integrate_kernel<5, 0, 4>;
+  if (v.groups == 8) return stream_integrate_kernel<5, 0, 8>;
+  if (v.minb == 4) return stream_integrate_kernel<4>;
+  if (v.minb == 6) return stream_integrate_kernel<6>;
+#endif
+  return stream_integrate_kernel<5>;
 }
 
 int stream_resident_blocks(int device) {
   if (device < 0 || device >= 64) return 0;
   if (g_resident_blocks[device] == 0) {
     int per_sm = 0, sms = 0;
-    const int minb = stream_min_blocks();
-    cudaError_t e = (minb == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_integrate_kernel<4>, kBlockThreads, 0)
-                  : (minb == 5) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_integrate_kernel<5>, kBlockThreads, 0)
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_integrate_kernel<6>, kBlockThreads, 0);
-    if (e != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_kernel(), kBlockThreads, 0) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+      return 0;
     g_resident_blocks[device] = per_sm * sms;
   }
   return g_resident_blocks[device];
@@ -629,25 +648,7 @@ cudaError_t launch_stream_cost(const StreamLaunch& L, cudaStream_t s) {
 
 cudaError_t launch_stream_integrate(const StreamLaunch& L, int n_blocks, cudaStream_t s) {
   if (n_blocks < 1) return cudaErrorInvalidValue;
-#ifdef TSDF_VALIDATION
-  if (const char* e = getenv("TSDF_STREAM_DIAG")) {   // diagnostic variants (see stream_integrate_kernel)
-    const int v = atoi(e);
-    if (v == 1) { stream_integrate_kernel<5, 1><<<n_blocks, kBlockThreads, 0, s>>>(L); return cudaGetLastError(); }
-    if (v == 2) { stream_integrate_kernel<5, 2><<<n_blocks, kBlockThreads, 0, s>>>(L); return cudaGetLastError(); }
-  }
-#endif
-  static const int groups = getenv("TSDF_STREAM_GROUPS") ? atoi(getenv("TSDF_STREAM_GROUPS")) : 1;
-  if (groups == 2 || groups == 4 || groups == 8) {   // A/B switch: phase B pooled over 128 / 64 / 32 threads
-    if (groups == 2) stream_integrate_kernel<5, 0, 2><<<n_blocks, kBlockThreads, 0, s>>>(L);
-    else if (groups == 4) stream_integrate_kernel<5, 0, 4><<<n_blocks, kBlockThreads, 0, s>>>(L);
-    else stream_integrate_kernel<5, 0, 8><<<n_blocks, kBlockThreads, 0, s>>>(L);
-    return cudaGetLastError();
-  }
-  switch (stream_min_blocks()) {
-    case 4: stream_integrate_kernel<4><<<n_blocks, kBlockThreads, 0, s>>>(L); break;
-    case 5: stream_integrate_kernel<5><<<n_blocks, kBlockThreads, 0, s>>>(L); break;
-    default: stream_integrate_kernel<6><<<n_blocks, kBlockThreads, 0, s>>>(L); break;
-  }
+  stream_kernel()<<<n_blocks, kBlockThreads, 0, s>>>(L);
   return cudaGetLastError();
 }
 
