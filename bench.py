@@ -424,7 +424,7 @@ def run_volume(args, D):
     # north-star's K-amortised HBM roofline line
     by_k = {}
     if (world == 1 or args.config == "1024") and slab_voxels * 8 < 40e9:
-        for k, nfr in ((1, min(F, 32)), (8, min(F, 64))):
+        for k, nfr in ((1, min(F, 64)), (8, min(F, 256))):
             v1 = make_volume((z0, z1), batch=k)
             v1.integrate_batch(depth, poses, n_frames=min(2 * k, F))
             v1.reset()
