@@ -381,6 +381,10 @@ void stream_group_params(const tsdf_volume* v, int ng, tsdf::StreamLaunch* L) {
   L->n_chunks = (ng + L->chunk - 1) / L->chunk;
   L->chunk = (ng + L->n_chunks - 1) / L->n_chunks;   // chunks of equal length (50 frames: 25 + 25, not 32 + 18)
   L->n_chunks = (ng + L->chunk - 1) / L->chunk;
+  if (L->epoch > 0) {   // epochs of equal length too (a 25-frame chunk: 7 + 6 + 6 + 6, not 8 + 8 + 8 + 1)
+    const int n_epochs = (L->chunk + L->epoch - 1) / L->epoch;
+    L->epoch = (L->chunk + n_epochs - 1) / n_epochs;
+  }
   L->cull_level = v->cull;
 }
 

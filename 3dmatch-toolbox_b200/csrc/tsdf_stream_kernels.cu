@@ -484,6 +484,17 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) stream_integrate_kernel(c
     // ---------------- write-back of the pending counts (certain free-space observations), coalesced ----------------
     // (after the last phase B: the float4 rows are re-read here, so they carry phase B's stores)
     if (frame_mask != 0u && DIAG != 1) {  // warp-uniform
+      // the rows the write-back will touch are prefetched into L2 first: with few frames per chunk the write-back is the
+      // HBM-bound part of the item, and the plane loop below (kept rolled: apply_pending is a data-dependent loop) has
+      // only one plane's loads in flight
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < ZT; ++k)
+          if (k < zcount && s_pend[k][threadIdx.x] != 0u) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tsdf + idx0 + k * plane));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(weight + idx0 + k * plane));
+          }
+      }
 #pragma unroll 1
       for (int k = 0; k < ZT; ++k) {
         const unsigned pk = s_pend[k][threadIdx.x];

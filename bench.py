@@ -969,7 +969,7 @@ def main():
     ap.add_argument("--rebalance", type=int, default=10, help="feedback-balancing warm-up steps for N > 1")
     ap.add_argument("--base-cost", type=float, default=0.05, help="cost of a fully culled z group relative to the mean group")
     ap.add_argument("--fragments", type=int, default=0, help="frag300: number of fragments (default 256)")
-    ap.add_argument("--frag-batch", type=int, default=8, help="frag300: fragments per launch")
+    ap.add_argument("--frag-batch", type=int, default=16, help="frag300: fragments per launch")
     ap.add_argument("--oracle-fragments", type=int, default=1, help="frag300: fragments per rank checked against the oracle")
     args = ap.parse_args()
     if args.impl == "reference":
