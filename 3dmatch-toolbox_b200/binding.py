@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "tsdf_point_cloud_to_tdf", "tsdf_integrate_multi", "tsdf_plan_z_cost", "tsdf_get_z_cost", "tsdf_split_slabs",
     "tsdf_sharded_create", "tsdf_sharded_destroy", "tsdf_sharded_reset", "tsdf_sharded_synchronize",
     "tsdf_sharded_integrate_batch", "tsdf_sharded_extract_surface", "tsdf_sharded_copy_surface", "tsdf_sharded_write_bin",
-    "tsdf_sharded_slab", "tsdf_copy_surface_normals", "tsdf_selftest_packed",
+    "tsdf_sharded_slab", "tsdf_copy_surface_normals", "tsdf_selftest_packed", "tsdf_selftest_pixel_margin",
 ]
 
 
@@ -119,6 +119,7 @@ def load_library(validation: bool = False) -> C.CDLL:
         "tsdf_device_count": [C.POINTER(C.c_int32)],
         "tsdf_selftest_rounding": [C.c_int32, i64p],
         "tsdf_selftest_packed": [C.c_int32, i64p],
+        "tsdf_selftest_pixel_margin": [C.c_int32, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -346,6 +347,13 @@ def selftest_packed(device=0) -> int:
     n = C.c_int64(-1)
     _check(load_library().tsdf_selftest_packed(device, C.byref(n)), "tsdf_selftest_packed")
     return n.value
+
+
+def selftest_pixel_margin(fx, c0, size, device=0):
+    """(max relative error of rcp.approx in units of 2^-24, max |u' - u| as a fraction of pixel_round_margin)."""
+    a, b = C.c_float(-1), C.c_float(-1)
+    _check(load_library().tsdf_selftest_pixel_margin(device, fx, c0, size, C.byref(a), C.byref(b)), "tsdf_selftest_pixel_margin")
+    return a.value, b.value
 
 
 def selftest_rounding(device=0) -> int:

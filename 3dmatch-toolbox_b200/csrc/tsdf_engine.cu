@@ -1236,6 +1236,23 @@ int tsdf_selftest_packed(int32_t device, int64_t* mismatches) {
   return TSDF_OK;
 }
 
+int tsdf_selftest_pixel_margin(int32_t device, float fx, float c0, float size, float* rcp_error_ulp24, float* worst_fraction) {
+  if (!rcp_error_ulp24 || !worst_fraction) return set_err(TSDF_ERR_ARG, "output pointer is NULL");
+  if (!(fx > 0.f) || !(size >= 1.f)) return set_err(TSDF_ERR_ARG, "fx and size must be positive");
+  CK(cudaSetDevice(device));
+  unsigned* d = nullptr;
+  CK(cudaMalloc(&d, 2 * sizeof *d));
+  CK(cudaMemset(d, 0, 2 * sizeof *d));
+  cudaError_t e = tsdf::launch_selftest_margin(d, fx, c0, size, 0);
+  float h[2] = {0.f, 0.f};
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CK(e);
+  *rcp_error_ulp24 = h[0];
+  *worst_fraction = h[1];
+  return TSDF_OK;
+}
+
 int tsdf_selftest_rounding(int32_t device, int64_t* mismatches) {
   if (!mismatches) return set_err(TSDF_ERR_ARG, "mismatches is NULL");
   CK(cudaSetDevice(device));

@@ -123,14 +123,23 @@ cudaError_t launch_stream_integrate(const StreamLaunch& L, int n_blocks, cudaStr
 // Only the per-z-group work counts (jobs[].zcost) of the frames in L; no masks, no item lists (slab planning).
 cudaError_t launch_stream_cost(const StreamLaunch& L, cudaStream_t s);
 
-// Bound on |u' - u| between the fast pixel coordinate u' = fma(cam, fx * rcp.approx(z), c0) and the
-// reference's u = fl(fl(fx * fl(cam / z)) + c0) for |u'| <= size + 1.5.  Relative errors: rcp.approx
-// <= 2^-23, every rounded product <= 2^-24, so fl(fx * fl(cam/z)) and cam * fl(fx * rcp(z)) differ by
-// at most 5 * 2^-24 * |fx cam / z| <= 2.98e-7 * (size + 1.5 + |c0|); the two final roundings add
-// 2 * 2^-24 * (size + 1.5).  The returned margin is twice that bound.
+// Bound on |u' - u| between the fast pixel coordinate u' = fma(cam, fl(fx * rcp.approx(z)), c0) and the reference's
+// u = fl(fl(fx * fl(cam / z)) + c0) (demo.cu:46-47) wherever the two can disagree about the pixel, i.e. for
+// u' in [-1.5, size + 1.5] (further out both round to a pixel outside the image, demo.cu:48).  With P = fx cam / z:
+//   reference   fl(cam / z) = (cam / z)(1 + d1), fl(fx * .) = (.)(1 + d2), |d| <= 2^-24, final sum + r1, |r1| <= 2^-24 |u|
+//   fast        rcp.approx(z) = (1 / z)(1 + e1): the PTX ISA bounds the ABSOLUTE error by 2^-23 on [1, 2), i.e. the
+//               relative error by 2^-22 = 4 * 2^-24 (the exponent is handled exactly; tsdf_selftest_pixel_margin measures it
+//               over every mantissa); fl(fx * .) = (.)(1 + e2), |e2| <= 2^-24; the fma rounds once: + r2, |r2| <= 2^-24 |u'|
+//   |u - u'| <= |P| (|d1| + |d2| + |e1| + |e2|) + |r1| + |r2| <= 7 * 2^-24 * pmax + 2 * 2^-24 * mag   (+ O(2^-46) terms)
+// where mag = size + 1.5 bounds |u|, |u'| and pmax = max |u' - c0| over that range bounds |P| (P is within the margin of
+// u' - c0).  The returned margin is 1.25 times that bound plus 1e-6; round 1 / 2 used the looser |P| <= mag + |c0| and a
+// factor 2, which sent 2.75 times as many voxels to the exact evaluation for nothing.  tsdf_selftest_pixel_margin() checks
+// the bound on 2.5e9 pseudo-random (cam, z) pairs per intrinsic set.
 __host__ __device__ inline float pixel_round_margin(float size, float c0) {
   const float mag = size + 1.5f;
-  return 2.0f * (2.98e-7f * (mag + (c0 < 0.f ? -c0 : c0)) + 1.2e-7f * mag) + 1e-6f;
+  const float a = c0 + 1.5f < 0.f ? -(c0 + 1.5f) : c0 + 1.5f, b = mag - c0 < 0.f ? c0 - mag : mag - c0;
+  const float pmax = (a > b ? a : b) + 1.0f;
+  return 1.25f * (4.1724e-7f * pmax + 1.1921e-7f * mag) + 1e-6f;
 }
 
 constexpr int kExtractTile = 4096;  // voxels per extraction tile (256 threads x 16)
@@ -159,6 +168,9 @@ cudaError_t launch_surface_normals(const ExtractParams& p, int64_t nz, const lon
                                    float* normals, cudaStream_t s);
 cudaError_t launch_selftest_rounding(unsigned long long* mismatches, cudaStream_t s);
 cudaError_t launch_selftest_packed(unsigned long long* mismatches, cudaStream_t s);   // tsdf_stream_kernels.cu
+// out2[0] / out2[1] (float bits, zeroed by the caller): max relative error of rcp.approx in units of 2^-24; max |u' - u| of
+// the fast pixel coordinate as a fraction of pixel_round_margin(size, c0)
+cudaError_t launch_selftest_margin(unsigned* out2, float fx, float c0, float size, cudaStream_t s);
 // tdf_kernels.cu: scratch = compute_tdf_scratch_bytes() bytes of device memory (two intermediate grids, 8 or 16 bit)
 size_t compute_tdf_scratch_bytes(int dim_x, int dim_y, int dim_z, int radius);
 cudaError_t launch_compute_tdf(const float* occ, float* tdf, void* scratch, int dim_x, int dim_y, int dim_z,

@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(kStreamMaxSegments) stream_segment_kernel(cons
 // ------------------------------------------------------------------------------------------------
 // DIAG (validation library only, results are NOT valid): 1 = no TSDF / weight traffic at all, so that every L2 read of
 // the launch is a depth gather (cache evidence in profiles/); 2 = depth gathers with an L2 evict_last cache hint (A/B).
+// (Measured and dropped: every thread prefetching the depth line of its first voxel in the warp's next frame into L1 --
+// 84.95 ms against 79.49 ms on the 256-frame run, profiles/r02_margin_and_prefetch_ab.txt.)
 // G: phase B is pooled over 256 / G threads: G = 1 the whole block (fullest lanes, one block barrier per epoch), G = 2 / 4
 // half / quarter blocks synchronised by named barriers (fewer warps wait for each other), G = 8 per warp (no barrier at
 // all, emptiest lanes).
@@ -546,6 +548,39 @@ __global__ void __launch_bounds__(256) selftest_packed_kernel(unsigned long long
   if (bad) atomicAdd(mismatches, bad);
 }
 
+// Self-test of pixel_round_margin(): (1) the relative error of rcp.approx.ftz.f32 over every mantissa of [1, 2) (the
+// exponent is handled exactly), in units of 2^-24; (2) |u' - u| between the fast pixel coordinate and the reference's
+// (demo.cu:46-47) on pseudo-random (cam, z) pairs whose pixel coordinate covers [-1.5, size + 1.5] and whose depth spans
+// 2^-6 .. 2^7, as a fraction of the margin.  out[0] = max of (1) as float bits, out[1] = max of (2) as float bits.
+__global__ void __launch_bounds__(256) selftest_margin_kernel(unsigned* __restrict__ out, float fx, float c0, float size,
+                                                              unsigned n_per_thread) {
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x, n_thr = gridDim.x * blockDim.x;
+  float worst_rcp = 0.0f, worst_u = 0.0f;
+  for (unsigned m = gid; m < (1u << 23); m += n_thr) {
+    const float x = __uint_as_float(0x3f800000u | m);
+    const double exact = 1.0 / (double)x;
+    worst_rcp = fmaxf(worst_rcp, (float)(fabs((double)rcp_approx(x) - exact) / exact * 16777216.0));
+  }
+  const float margin = pixel_round_margin(size, c0);
+  unsigned long long state = 0xD1B54A32D192ED03ull * ((unsigned long long)gid + 1ull);
+  for (unsigned i = 0; i < n_per_thread; ++i) {
+    state += 0x9E3779B97F4A7C15ull;
+    unsigned long long z64 = state;
+    z64 = (z64 ^ (z64 >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z64 = (z64 ^ (z64 >> 27)) * 0x94D049BB133111EBull;
+    z64 ^= z64 >> 31;
+    const float u_t = -1.5f + (size + 3.0f) * ((float)(unsigned)(z64 >> 40) * (1.0f / 16777216.0f));
+    const float zm = 1.0f + (float)(unsigned)((z64 >> 16) & 0xffffffu) * (1.0f / 16777216.0f);   // [1, 2)
+    const float z = zm * __uint_as_float(((unsigned)(z64 & 15u) + 121u) << 23);                 // x 2^-6 .. 2^9
+    const float cam = (u_t - c0) * z / fx;
+    const float u_ref = __fadd_rn(__fmul_rn(fx, __fdiv_rn(cam, z)), c0);                         // demo.cu:46
+    const float u_fast = __fmaf_rn(cam, __fmul_rn(rcp_approx(z), fx), c0);                       // voxel_classify_pair
+    if (u_fast >= -1.5f && u_fast <= size + 1.5f) worst_u = fmaxf(worst_u, fabsf(u_fast - u_ref) / margin);
+  }
+  atomicMax(out + 0, __float_as_uint(worst_rcp));   // (non-negative floats order like their bit patterns)
+  atomicMax(out + 1, __float_as_uint(worst_u));
+}
+
 int g_resident_blocks[64] = {};
 
 }  // namespace
@@ -646,6 +681,11 @@ cudaError_t launch_stream_masks(const StreamLaunch& L, cudaStream_t s) {
 
 cudaError_t launch_selftest_packed(unsigned long long* mismatches, cudaStream_t s) {
   selftest_packed_kernel<<<148 * 8, 256, 0, s>>>(mismatches, 4096);   // 2.5e9 lanes
+  return cudaGetLastError();
+}
+
+cudaError_t launch_selftest_margin(unsigned* out2, float fx, float c0, float size, cudaStream_t s) {
+  selftest_margin_kernel<<<148 * 8, 256, 0, s>>>(out2, fx, c0, size, 8192);   // 2.5e9 pairs
   return cudaGetLastError();
 }
 

@@ -235,6 +235,13 @@ int tsdf_selftest_rounding(int32_t device, int64_t *mismatches);
 /* Device self-test of the packed (f32x2) set-up arithmetic of the fusion kernel against the scalar round-to-nearest
  * intrinsics (one IEEE rounding per operation of demo.cu:35-41) on 2.5e9 pseudo-random lanes; 0 expected. */
 int tsdf_selftest_packed(int32_t device, int64_t *mismatches);
+/* Device self-test of the pixel-rounding margin of the fast classification (the bound on the difference between the
+ * kernel's pixel coordinate and the reference's, demo.cu:46-47): *rcp_error_ulp24 receives the largest relative error
+ * of rcp.approx over every mantissa in units of 2^-24 (the bound assumes <= 4), *worst_fraction the largest observed
+ * difference on 2.5e9 pseudo-random (cam, z) pairs for the intrinsics (fx, c0) and image extent `size`, as a fraction
+ * of the margin (must stay below 1; the derivation leaves a factor 1.25). */
+int tsdf_selftest_pixel_margin(int32_t device, float fx, float c0, float size, float *rcp_error_ulp24,
+                               float *worst_fraction);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,18 @@ def test_packed_setup_arithmetic_is_two_roundings(pkg):
     assert pkg.binding.selftest_packed(0) == 0
 
 
+@pytest.mark.parametrize("fx,c0,size", [(585.0, 320.0, 640.0), (585.0, 240.0, 480.0), (1050.0, 100.5, 1280.0),
+                                         (320.0, 700.0, 640.0)])
+def test_pixel_round_margin_bounds_the_fast_pixel_coordinate(pkg, fx, c0, size):
+    """pixel_round_margin() (tsdf_kernels.h) is derived from |rel. error of rcp.approx| <= 4 * 2^-24 and leaves a factor
+    1.25: measured over every mantissa / on 2.5e9 pseudo-random (cam, z) pairs per intrinsic set (principal point inside,
+    off-centre and outside the image)."""
+    rcp_err, worst = pkg.binding.selftest_pixel_margin(fx, c0, size)
+    assert 0.0 < rcp_err <= 4.0, rcp_err
+    assert 0.0 < worst <= 0.8, worst
+    print(f"rcp.approx max relative error {rcp_err:.3f} x 2^-24; worst |u' - u| = {worst:.3f} of the margin")
+
+
 def test_rounding_helper_all_float_bit_patterns(pkg):
     """round_pixel() == roundf() + the reference bounds test (demo.cu:46-49) for all 2^32 floats."""
     assert pkg.binding.selftest_rounding(0) == 0
