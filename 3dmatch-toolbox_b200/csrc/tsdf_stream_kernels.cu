@@ -588,7 +588,7 @@ int g_resident_blocks[64] = {};
 bool stream_prepare_geometry(StreamLaunch* L) {
   if (L->dim_x % VEC != 0 || !(L->trunc_margin > 0.0f) || (int64_t)L->im_w * L->im_h >= (1 << 22)) return false;
   if (L->chunk < 1 || L->chunk > kChunkMax) return false;
-  if (L->epoch < 1) L->epoch = 8;
+  if (L->epoch < 1) L->epoch = 16;   // (8 / 11 / 16 / 32: 79.4 / 78.9 / 78.5 / 78.8 ms on the 256-frame run)
   L->plan_beta = 3;   // (calibrated on the 1024^3 workload, profiles/README.md)
   if (const char* e = getenv("TSDF_PLAN_BETA")) {
     const int v = atoi(e);

@@ -66,6 +66,8 @@ def main():
     lz = np.arange(TZ)[:, None, None]
     tot = dict(out=0, invalid=0, behind=0, free=0, band=0)
     kept_now = kept_aniso = kept_ideal = kept_frustum = 0
+    kept_multi = useful_multi = 0
+    MAXB = int(sys.argv[4]) if len(sys.argv) > 4 else 12
     vox_now = vox_aniso = 0
     useful_now = useful_aniso = 0
     n_pairs = 0
@@ -131,6 +133,19 @@ def main():
                     m = an[fi][(a, b)]
                     dmax = max(m[y0 // b, x0 // a], m[y0 // b, x1 // a], m[y1 // b, x0 // a], m[y1 // b, x1 // a])
                     aniso = not (dmax + tr * 1.0001 <= czmin)
+                # (c) finest square level whose block grid over the bounding box has at most MAXB blocks
+                multi = True
+                for l, sz in enumerate(levels):
+                    bx0, bx1, by0, by1 = x0 // sz, x1 // sz, y0 // sz, y1 // sz
+                    if (bx1 - bx0 + 1) * (by1 - by0 + 1) <= MAXB:
+                        dmax = sq[fi][l][by0:by1 + 1, bx0:bx1 + 1].max()
+                        multi = not (dmax + tr * 1.0001 <= czmin)
+                        break
+            if not pos.all():
+                multi = True
+            kept_multi += multi
+            useful_multi += (multi and useful)
+            assert (not useful) or multi
             for k, n in zip(("out", "invalid", "behind", "free", "band"), (n_out, n_inv, n_b, n_f, n_band)):
                 if now:
                     tot[k] += n
@@ -144,6 +159,7 @@ def main():
     print(f"  in frustum (any voxel in the image): {kept_frustum / n_pairs:.3f}")
     print(f"  kept by the engine's test:           {kept_now / n_pairs:.3f}   of which useful {useful_now / max(kept_now, 1):.3f}")
     print(f"  kept by the anisotropic pyramid:     {kept_aniso / n_pairs:.3f}   of which useful {useful_aniso / max(kept_aniso, 1):.3f}")
+    print(f"  kept by <= {MAXB} blocks of the finest level: {kept_multi / n_pairs:.3f}   of which useful {useful_multi / max(kept_multi, 1):.3f}")
     print(f"  ideal (tile holds an updated voxel): {kept_ideal / n_pairs:.3f}")
     s = sum(tot.values())
     print("  voxels of the kept pairs: " + ", ".join(f"{k} {v / s:.3f}" for k, v in tot.items()))
