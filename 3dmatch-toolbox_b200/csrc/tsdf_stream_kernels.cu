@@ -79,7 +79,8 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 // ------------------------------------------------------------------------------------------------
 // kCostOnly: no masks / items are written, only the per-z-group counts of kept (warp tile, frame) pairs (slab planning).
 template <bool kCostOnly>
-__global__ void __launch_bounds__(256) stream_mask_kernel(const __grid_constant__ StreamLaunch L) {
+__global__ void __launch_bounds__(256, TSDF_MASK_MINB) stream_mask_kernel(const __grid_constant__ StreamLaunch L) {
+  __shared__ uint2 s_ballot[256 / 32][kWarps];   // (keep, interior) ballots of the warp's eight warp tiles
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gw >= (int64_t)L.n_jobs * L.n_btiles) return;
@@ -123,17 +124,28 @@ __global__ void __launch_bounds__(256) stream_mask_kernel(const __grid_constant_
         box_frame_test(L, K, ps, mips_f, x_lo, x_hi, yb_lo, yb_hi, z_lo, z_hi, bk, bi);
       }
       if (__any_sync(0xffffffffu, bk)) {
-#pragma unroll
+        // (kept rolled: eight inlined copies of the test made the kernel 94 KB of SASS and the instruction cache its
+        //  bottleneck -- 48 % of the stall samples were no_instructions; the ballots go through shared memory because a
+        //  rolled loop cannot index a register array)
+#pragma unroll 1
         for (int w = 0; w < kWarps; ++w) {
           const int y_lo = yb_lo + w * rows_per_warp;
           bool k = false, i = false, nr = false;
           if (bk && y_lo < L.dim_y)
             box_frame_test(L, K, ps, mips_f, x_lo, x_hi, y_lo, min(L.dim_y - 1, y_lo + rows_per_warp - 1), z_lo, z_hi, k, i, &nr);
-          keep_w[w] = __ballot_sync(0xffffffffu, k);
-          in_w[w] = __ballot_sync(0xffffffffu, i);
+          const unsigned kb = __ballot_sync(0xffffffffu, k), ib = __ballot_sync(0xffffffffu, i);
+          if (lane == 0) s_ballot[threadIdx.x >> 5][w] = make_uint2(kb, ib);
           // work statistics: a tile that reaches the band of the farthest surface behind it pays for exact evaluations
           cost += (unsigned long long)L.plan_beta * (unsigned)__popc(__ballot_sync(0xffffffffu, nr));
         }
+        __syncwarp();
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const uint2 b = s_ballot[threadIdx.x >> 5][w];
+          keep_w[w] = b.x;
+          in_w[w] = b.y;
+        }
+        __syncwarp();
       }
     }
 #pragma unroll

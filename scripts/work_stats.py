@@ -15,6 +15,7 @@ contain no voxel that is updated at all.
   python scripts/work_stats.py [n_tiles] [n_frames] [config]
 """
 import importlib.util
+import os
 import sys
 from pathlib import Path
 
@@ -58,7 +59,7 @@ def main():
     c2w, b2w = synth.make_poses(frames)
     poses = [np.linalg.inv(b2w.astype(np.float64)) @ m.astype(np.float64) for m in c2w]
 
-    TX, TY, TZ = 32, 4, 8
+    TX, TY, TZ = (int(v) for v in os.environ.get('TILE', '32,4,8').split(','))
     ntx, nty, ntz = dx // TX, dy // TY, dz // TZ
     tiles = np.stack([rng.integers(0, ntx, n_tiles), rng.integers(0, nty, n_tiles), rng.integers(0, ntz, n_tiles)], 1)
     lx = np.arange(TX)[None, None, :]
@@ -67,6 +68,9 @@ def main():
     tot = dict(out=0, invalid=0, behind=0, free=0, band=0)
     kept_now = kept_aniso = kept_ideal = kept_frustum = 0
     kept_multi = useful_multi = 0
+    ZGS = ()
+    sub_tot = {z: 0 for z in ZGS}
+    sub_kept = {z: 0 for z in ZGS}
     MAXB = int(sys.argv[4]) if len(sys.argv) > 4 else 12
     vox_now = vox_aniso = 0
     useful_now = useful_aniso = 0
@@ -145,6 +149,30 @@ def main():
                 multi = True
             kept_multi += multi
             useful_multi += (multi and useful)
+            if multi:
+                # z-granular refinement: groups of ZG planes of the kept tile, same test on the group's voxels
+                U, V, CZ, INB = (a.reshape(TZ, TY * TX) for a in (u, v, czv, inb))
+                upd = (free | band).reshape(TZ, TY * TX)
+                for zg in ZGS:
+                    for g0 in range(0, TZ, zg):
+                        sl = slice(g0, g0 + zg)
+                        sub_tot[zg] += 1
+                        if not INB[sl].any():
+                            continue
+                        keep = True
+                        if pos.all():
+                            gx0, gx1 = max(0, int(np.floor(U[sl].min() - 1.5))), min(W - 1, int(np.ceil(U[sl].max() + 1.5)))
+                            gy0, gy1 = max(0, int(np.floor(V[sl].min() - 1.5))), min(H - 1, int(np.ceil(V[sl].max() + 1.5)))
+                            if gx1 < gx0 or gy1 < gy0:
+                                keep = False
+                            else:
+                                for l, sz in enumerate(levels):
+                                    b0, b1, c0, c1 = gx0 // sz, gx1 // sz, gy0 // sz, gy1 // sz
+                                    if (b1 - b0 + 1) * (c1 - c0 + 1) <= MAXB:
+                                        keep = not (sq[fi][l][c0:c1 + 1, b0:b1 + 1].max() + tr * 1.0001 <= CZ[sl].min())
+                                        break
+                        sub_kept[zg] += keep
+                        assert keep or not upd[sl].any()
             assert (not useful) or multi
             for k, n in zip(("out", "invalid", "behind", "free", "band"), (n_out, n_inv, n_b, n_f, n_band)):
                 if now:
@@ -160,6 +188,8 @@ def main():
     print(f"  kept by the engine's test:           {kept_now / n_pairs:.3f}   of which useful {useful_now / max(kept_now, 1):.3f}")
     print(f"  kept by the anisotropic pyramid:     {kept_aniso / n_pairs:.3f}   of which useful {useful_aniso / max(kept_aniso, 1):.3f}")
     print(f"  kept by <= {MAXB} blocks of the finest level: {kept_multi / n_pairs:.3f}   of which useful {useful_multi / max(kept_multi, 1):.3f}")
+    for z in ZGS:
+        print(f"    of the kept tiles' groups of {z} plane(s), kept by the same test: {sub_kept[z] / max(sub_tot[z], 1):.3f}")
     print(f"  ideal (tile holds an updated voxel): {kept_ideal / n_pairs:.3f}")
     s = sum(tot.values())
     print("  voxels of the kept pairs: " + ", ".join(f"{k} {v / s:.3f}" for k, v in tot.items()))
