@@ -426,8 +426,8 @@ def run_volume(args, D):
     if (world == 1 or args.config == "1024") and slab_voxels * 8 < 40e9:
         for k, nfr in ((1, min(F, 64)), (8, min(F, 256))):
             v1 = make_volume((z0, z1), batch=k)
-            v1.integrate_batch(depth, poses, n_frames=min(2 * k, F))
-            v1.reset()
+            v1.integrate_batch(depth, poses, n_frames=nfr)   # the same call once untimed: the lazy allocations (frame
+            v1.reset()                                       # store, masks, item lists for nfr frames) happen here
             v1.synchronize()
             ms_k = D.max(time_step(v1, lambda: v1.integrate_batch(depth, poses, n_frames=nfr), D))
             v1.close()
@@ -436,6 +436,16 @@ def run_volume(args, D):
                             "updates_per_sec": total_voxels * nfr / (ms_k * 1e-3)}
     by_k[str(K)] = {"frames": F, "ms": round(ms_int, 3), "achieved": round(achieved, 1), "frac": round(achieved / peak, 4),
                     "updates_per_sec": total_voxels * F / (ms_int * 1e-3)}
+
+    # the north-star's line: fraction of the K-amortised HBM roofline (16 B per voxel per pass) at K = 8, the batch size it
+    # was written for, next to the production K
+    target = None
+    if "8" in by_k:
+        target = {"hbm_roofline_target_frac": 0.70, "k8_mode_frac": by_k["8"]["frac"], "k8_mode_updates_per_sec": by_k["8"]["updates_per_sec"],
+                  f"k{K}_frac": by_k[str(K)]["frac"], f"k{K}_updates_per_sec": by_k[str(K)]["updates_per_sec"],
+                  "note": "the ceiling peak x K / 16 rises with K, the cost of classifying a voxel does not: K = 8 sits at the HBM "
+                          "ceiling (culled voxels are never loaded, so the algorithmic-bytes figure can exceed 1), the production "
+                          "K = 32 is faster in absolute terms and bound by instruction issue (roofline_issue)"}
 
     # ---- e2e: host buffers through the C ABI, H2D + fusion + extraction + D2H of the points ---------
     e2e, gathered_cloud = run_e2e(args, D, pkg, vol, depth, poses, ranges, total_voxels, F)
@@ -466,7 +476,7 @@ def run_volume(args, D):
                        "slabs": [list(map(int, r)) for r in ranges], "rank_ms_per_step": rank_ms,
                        "sum_rank_ms": round(sum(rank_ms), 1), "rebalance_warmup_ms": rebalance_log, "plan_ms": plan_ms},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_dram": roofline_dram,
-            "roofline_issue": roofline_issue, "roofline_by_k": by_k, "parity": parity,
+            "roofline_issue": roofline_issue, "roofline_by_k": by_k, "north_star_target": target, "parity": parity,
             "cpu_baseline": cpu, "ref_cuda_kernel_baseline": ref_cuda, "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
