@@ -391,8 +391,10 @@ def run_volume(args, D):
     n_pass = -(-F // K)                    # passes over the volume = chunks
     n_launch = -(-F // 1024)               # persistent launches (groups of <= 1024 frames)
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = BYTES_PER_VOXEL_PASS * slab_voxels * n_pass
-    achieved = alg_bytes / (ms_int * 1e-3) / 1e9
+    # N > 1: the whole job's bytes over the slowest rank's time, per GPU (a per-rank figure would credit the rank that
+    # holds the cheap near slab with bytes it never had to move)
+    alg_bytes = BYTES_PER_VOXEL_PASS * total_voxels * n_pass
+    achieved = alg_bytes / (ms_int * 1e-3) / 1e9 / world
     ctr = kernel_counters(f"{args.config}_k{K}") or {}
     sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
@@ -401,7 +403,7 @@ def run_volume(args, D):
                 "peak_source": peak_src, "kernel": "stream_integrate_kernel (persistent, one launch per <= 1024 frames)",
                 "frames_per_pass": K, "passes_per_launch": n_pass / n_launch, "launches": n_launch,
                 "algorithmic_bytes_per_launch": alg_bytes / n_launch, "avg_launch_ms": round(ms_int / n_launch, 3),
-                "updates_per_sec_roofline": peak * 1e9 / BYTES_PER_VOXEL_PASS * K,
+                "updates_per_sec_roofline": peak * 1e9 / BYTES_PER_VOXEL_PASS * K * world, "per_gpu": world > 1,
                 "binding": "instruction issue, not HBM: the kernel never loads voxels no frame observes and amortises "
                            "the volume pass over K frames, so the algorithmic-bytes ceiling (peak x K / 16 updates/s) "
                            "rises with K while the per-voxel classification cost does not; see roofline_issue"}
@@ -431,7 +433,7 @@ def run_volume(args, D):
             v1.synchronize()
             ms_k = D.max(time_step(v1, lambda: v1.integrate_batch(depth, poses, n_frames=nfr), D))
             v1.close()
-            ach = BYTES_PER_VOXEL_PASS * slab_voxels * (-(-nfr // k)) / (ms_k * 1e-3) / 1e9
+            ach = BYTES_PER_VOXEL_PASS * total_voxels * (-(-nfr // k)) / (ms_k * 1e-3) / 1e9 / world
             by_k[str(k)] = {"frames": nfr, "ms": round(ms_k, 3), "achieved": round(ach, 1), "frac": round(ach / peak, 4),
                             "updates_per_sec": total_voxels * nfr / (ms_k * 1e-3)}
     by_k[str(K)] = {"frames": F, "ms": round(ms_int, 3), "achieved": round(achieved, 1), "frac": round(achieved / peak, 4),
