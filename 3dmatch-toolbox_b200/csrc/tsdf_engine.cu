@@ -507,7 +507,9 @@ int stream_integrate(tsdf_volume* v, int n_frames, const Src* src, const float* 
   int group_max = (kind == MemKind::Device) ? kStreamGroupDevice : kStreamGroupHost;
   if (group_max > seg_cap) group_max = seg_cap;
   // host input: the first group is small so that the fusion starts after a short upload, the following ones grow (fewer
-  // launch tails); every group's upload overlaps the fusion of the previous one
+  // launch tails); every group's upload overlaps the fusion of the previous one.  (Measured, scripts/e2e_breakdown.py,
+  // 1024^3 x 1000 frames: device input 275.1 ms, device input in this group schedule 276.8 ms, pinned host input
+  // 298.4 ms; growing by 7/4 from 16 frames instead of 3 from 32 changes nothing: 299.7 ms.)
   int group = (kind == MemKind::Device) ? group_max : (group_max < 32 ? group_max : 32);
   for (int g0 = 0, ng = 0; g0 < n_frames; g0 += ng) {
     ng = (n_frames - g0 < group) ? n_frames - g0 : group;
