@@ -352,9 +352,11 @@ int stream_prepare_job(tsdf_volume* v, StreamSlot& S, int ng, const float* cam2b
   if (S.staged) CK(cudaEventSynchronize(S.ev_staged));
   for (int f = 0; f < ng; ++f) pose_from_cam2base(cam2base + 16 * (size_t)f, &S.poses_pin[f]);
   stream_cull_margins(v->max_abs_corner, S.poses_pin, ng, L);
-  CK(cudaMemcpyAsync(S.poses_dev, S.poses_pin, (size_t)ng * sizeof(tsdf::FramePose), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(S.counters, 0, kCounterWords * sizeof(unsigned), st));
-  CK(cudaMemsetAsync(S.progress, 0, (size_t)L->n_btiles * sizeof(unsigned), st));
+  // (kernels, not the copy engine: see launch_small_copy)
+  CK(tsdf::launch_small_copy(S.poses_dev, S.poses_pin, (size_t)ng * sizeof(tsdf::FramePose), st));
+  CK(tsdf::launch_small_copy(S.counters, nullptr, kCounterWords * sizeof(unsigned), st));
+  CK(tsdf::launch_small_copy(S.progress, nullptr, (size_t)L->n_btiles * sizeof(unsigned), st));
+  v->stats.kernel_launches += 3;
   if (v->cull >= 2) {
     CK(tsdf::launch_build_depth_mips(S.depth, S.mips, ng, v->d.im_width, v->d.im_height, v->frame_px, st));
     v->stats.kernel_launches += 1;
@@ -445,7 +447,8 @@ int stream_fuse_group(tsdf_volume* v, StreamSlot& S, int ng, const float* cam2ba
     L.z_reverse = ((tz / (float)ng) < mid) ? 1 : 0;
   }
   *S.job_pin = job;
-  CK(cudaMemcpyAsync(S.job_dev, S.job_pin, sizeof job, cudaMemcpyHostToDevice, v->stream));
+  CK(tsdf::launch_small_copy(S.job_dev, S.job_pin, sizeof job, v->stream));
+  v->stats.kernel_launches += 1;
   CK(cudaEventRecord(S.ev_staged, v->stream));
   S.staged = true;
   L.jobs = S.job_dev;
@@ -1069,7 +1072,8 @@ int tsdf_integrate_multi(tsdf_volume* const* vols, int32_t n_vols, int32_t n_fra
     const float mid = lead->d.origin_z + 0.5f * (float)(lead->d.z_begin + lead->d.z_end) * lead->d.voxel_size;
     L.z_reverse = ((tz / ((float)n_frames * (float)n_vols)) < mid) ? 1 : 0;
   }
-  CK(cudaMemcpyAsync(LS.job_dev, LS.job_pin, (size_t)n_vols * sizeof(tsdf::StreamJob), cudaMemcpyHostToDevice, lead->stream));
+  CK(tsdf::launch_small_copy(LS.job_dev, LS.job_pin, (size_t)n_vols * sizeof(tsdf::StreamJob), lead->stream));
+  lead->stats.kernel_launches += 1;
   CK(cudaEventRecord(LS.ev_staged, lead->stream));
   LS.staged = true;
   L.jobs = LS.job_dev;

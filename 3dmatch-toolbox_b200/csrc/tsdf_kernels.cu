@@ -1280,6 +1280,25 @@ cudaError_t launch_surface_normals(const ExtractParams& p, int64_t nz, const lon
   return cudaGetLastError();
 }
 
+// Small host -> device transfers of the stream path (poses, job descriptors) and the zeroing of its counters, as a KERNEL
+// on the fusion stream instead of cudaMemcpyAsync / cudaMemsetAsync: the copy engine executes what became runnable
+// first, and a 48-byte pose copy that becomes runnable together with the next group's 300 MB frame upload waited behind
+// it -- the whole upload ended up serialised with the fusion (CUPTI timeline, profiles/r02_e2e_timeline.txt).  `src` is
+// pinned host memory (cudaHostAlloc: device-accessible under unified addressing) or nullptr for a zero fill.
+__global__ void __launch_bounds__(256) small_copy_kernel(unsigned* __restrict__ dst, const unsigned* src, int64_t n_words) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src ? src[i] : 0u;
+}
+
+cudaError_t launch_small_copy(void* dst, const void* pinned_src_or_null, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return cudaSuccess;
+  if (bytes % 4 != 0) return cudaErrorInvalidValue;
+  const int64_t n = (int64_t)(bytes / 4);
+  const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+  small_copy_kernel<<<blocks, 256, 0, s>>>(static_cast<unsigned*>(dst), static_cast<const unsigned*>(pinned_src_or_null), n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_selftest_rounding(unsigned long long* mismatches, cudaStream_t s) {
   selftest_rounding_kernel<<<148 * 16, 256, 0, s>>>(mismatches);
   return cudaGetLastError();

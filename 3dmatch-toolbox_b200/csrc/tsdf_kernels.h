@@ -166,6 +166,8 @@ cudaError_t launch_extract_emit(const ExtractParams& p, const unsigned long long
 // Unit normals (normalised central TSDF differences) of n surface voxels given by their slab-local linear indices.
 cudaError_t launch_surface_normals(const ExtractParams& p, int64_t nz, const long long* voxel_index, int64_t n,
                                    float* normals, cudaStream_t s);
+// dst <- pinned host memory (or zeros when the source is nullptr), `bytes` a multiple of 4, by a kernel on `s` (not the copy engine)
+cudaError_t launch_small_copy(void* dst, const void* pinned_src_or_null, size_t bytes, cudaStream_t s);
 cudaError_t launch_selftest_rounding(unsigned long long* mismatches, cudaStream_t s);
 cudaError_t launch_selftest_packed(unsigned long long* mismatches, cudaStream_t s);   // tsdf_stream_kernels.cu
 // out2[0] / out2[1] (float bits, zeroed by the caller): max relative error of rcp.approx in units of 2^-24; max |u' - u| of
